@@ -1,0 +1,11 @@
+"""humanvid_b200 -- Blackwell-native (sm_100a) denoising path of CamAnimate / HumanVid.
+
+Public surface mirrors the reference's modules for this path (see modules.py / pipeline.py); the arithmetic lives in
+lib/libhv_b200.so, built by ``__graft_entry__.build()``.
+"""
+from .modules import (CameraPoseEncoder, PoseGuider, ReferenceAttentionControl, TemporalBasicTransformerBlock, UNet3DConditionModel,
+                      UNet3DConditionOutput)
+from .scheduler import DDIMScheduler
+
+__all__ = ["UNet3DConditionModel", "UNet3DConditionOutput", "PoseGuider", "CameraPoseEncoder", "ReferenceAttentionControl",
+           "TemporalBasicTransformerBlock", "DDIMScheduler"]

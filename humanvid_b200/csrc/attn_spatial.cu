@@ -1,0 +1,321 @@
+// Spatial multi-head self-attention over the tokens of one frame (reference: diffusers Attention + AttnProcessor2_0
+// reached from src/models/attention.py:405-408, and the ReferenceAttentionControl read hook
+// src/models/mutual_self_attention.py:147-186 that appends the reference image's tokens as extra keys/values).
+//
+// Flash-style, tcgen05: one CTA per (128-query tile, head, frame).
+//   warp 0      TMA producer : Q tile once, then K / V^T tiles of 128 keys through a shared-memory ring
+//   warp 1      MMA issuer   : S = Q K^T (UMMA 128x128xdpad) into TMEM, then PV = P V (UMMA 128 x dpad x 128) into TMEM
+//   warps 2..5  softmax      : one query row per thread: tcgen05.ld S, running max / sum in registers, P (fp16) written
+//                              to shared memory in the 128B-swizzled K-major layout the next UMMA reads, PV tile read back
+//                              from TMEM and accumulated into fp32 registers with the online-softmax rescale
+// Keys come from two segments: the frame's own L tokens and, for frames of the conditional CFG half, the Lb tokens of
+// the batch item's reference bank -- the reference instead materialises cat([x, bank.repeat(F)]) per frame and
+// recomputes the unconditional half (mutual_self_attention.py:158-186).
+// V is consumed transposed (V^T[channel][token], produced directly by a GEMM with swapped operands) so every UMMA
+// operand in this file is K-major and shares one shared-memory descriptor format with gemm.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tma.h"
+
+namespace hv {
+
+namespace {
+
+constexpr int ATT_THREADS = 192;
+constexpr int QT = 128;   // queries per CTA
+constexpr int KT = 128;   // keys per tile
+
+template <int D>
+struct ACfg {
+  static constexpr int kDpad = (D + 15) / 16 * 16;
+  static constexpr int kKC = (kDpad + 63) / 64;               // 64-column chunks of Q / K rows
+  static constexpr int kQBytes = kKC * QT * 128;
+  static constexpr int kKBytes = kKC * KT * 128;
+  static constexpr int kVChunk = kDpad * 128;                  // [dpad rows][64 keys]
+  static constexpr int kVBytes = 2 * kVChunk;
+  static constexpr int kPBytes = 2 * QT * 128;                 // two 64-key chunks
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kStages = (kQBytes + kPBytes + 2 * kStageBytes + 2048 <= 227 * 1024) ? 2 : 1;
+  static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 256 + 1024;
+  static constexpr int kTmemCols = (128 + kDpad) <= 256 ? 256 : 512;
+  static constexpr int kMinBlocks = (2 * kSmemBytes <= 227 * 1024 && kTmemCols == 256) ? 2 : 1;
+};
+
+struct AttnKernelArgs {
+  __half* out;
+  long long ldo;
+  int L, Lb, F, nf_nobank, heads;
+  int vt_stride, vbt_stride;
+  float scale_log2;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, ACfg<D>::kMinBlocks)
+attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+            const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
+            const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
+  using C = ACfg<D>;
+  constexpr int DP = C::kDpad;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + C::kQBytes;
+  uint8_t* sKV = sP + C::kPBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::kStages * C::kStageBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_pv = bars + 3;
+  uint64_t* bar_kv_full = bars + 4;
+  uint64_t* bar_kv_empty = bars + 4 + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * C::kStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
+  const int Ts = (a.L + KT - 1) / KT;
+  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
+  const int bidx = n / a.F;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_pv, 1);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&bar_kv_full[s], 1);
+      mbar_init(&bar_kv_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;          // 128 columns: S tile
+  const uint32_t tmem_pv = tmem_base + 128;   // DP columns: P V tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, C::kQBytes);
+#pragma unroll
+      for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sQ + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * C::kStageBytes;
+        uint8_t* sV = sK + C::kKBytes;
+        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
+        const bool self = j < Ts;
+        const CUtensorMap* mk = self ? &map_k : &map_kb;
+        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
+        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;           // K rows
+        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;  // V^T columns (16B aligned)
+#pragma unroll
+        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
+        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * D);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * D);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DP);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      auto issue_s = [&](int stage) {
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
+          umma_f16_ss(tmem_s, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_s);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(bar_p, j & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
+          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
+          umma_f16_ss(tmem_pv, ad, bd, idesc_pv, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_pv);
+        umma_commit(&bar_kv_empty[stage]);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (j + 1 < T) {
+          mbar_wait(&bar_kv_full[stage], phase);
+          tc_fence_after();
+          issue_s(stage);
+        }
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    float o[DP];
+#pragma unroll
+    for (int c = 0; c < DP; ++c) o[c] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < T; ++j) {
+      const bool self = j < Ts;
+      const int kv_valid = self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT);
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_s + lane_off + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float m_new = fmaxf(m, mx * a.scale_log2);
+      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
+      // pass 2: p = exp2(s*scale - m_new) -> fp16 -> swizzled smem; row sum of the ROUNDED p (what the MMA consumes)
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_s + lane_off + c * 32, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c0 = c * 32 + 2 * i;
+          float p0 = c0 < kv_valid ? fast_exp2(__uint_as_float(raw[2 * i]) * a.scale_log2 - m_new) : 0.f;
+          float p1 = c0 + 1 < kv_valid ? fast_exp2(__uint_as_float(raw[2 * i + 1]) * a.scale_log2 - m_new) : 0.f;
+          __half2 hp = __floats2half2_rn(p0, p1);
+          float2 back = __half22float2(hp);
+          psum += back.x + back.y;
+          pk[i] = *reinterpret_cast<uint32_t*>(&hp);
+        }
+        // 32 keys = 4 units of 16 B inside 64-key chunk (c / 2), units (c % 2) * 4 + u
+        uint8_t* chunk = prow + (c >> 1) * (QT * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (c & 1) * 4 + u;
+          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      }
+      l = l * alpha + psum;
+      m = m_new;
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      // accumulate this tile's P V
+      mbar_wait(bar_pv, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < DP / 16; ++c) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_pv + lane_off + c * 16, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c * 16 + i] = o[c * 16 + i] * alpha + __uint_as_float(raw[i]);
+      }
+    }
+    tc_fence_before();
+    if (q0 + r < a.L) {
+      const float inv = 1.f / l;
+      __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        uint4 u;
+        u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+        u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+        u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+        u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int D>
+cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
+  using C = ACfg<D>;
+  CUtensorMap mq, mk, mvt, mkb, mvbt;
+  const long long tokens = static_cast<long long>(a.NF) * a.L;
+  if (!make_map_2d(&mq, a.q, tokens, a.ldq, a.ldq, QT)) return cudaErrorInvalidValue;
+  if (!make_map_2d(&mk, a.k, tokens, a.ldk, a.ldk, KT)) return cudaErrorInvalidValue;
+  if (!make_map_2d(&mvt, a.vt, static_cast<long long>(a.heads) * D, static_cast<long long>(a.NF) * a.vt_stride, a.ldvt, C::kDpad)) return cudaErrorInvalidValue;
+  mkb = mk;
+  mvbt = mvt;
+  const int B = a.NF / (a.F > 0 ? a.F : 1);
+  if (a.Lb > 0) {
+    if (!make_map_2d(&mkb, a.kb, static_cast<long long>(B) * a.Lb, a.ldkb, a.ldkb, KT)) return cudaErrorInvalidValue;
+    if (!make_map_2d(&mvbt, a.vbt, static_cast<long long>(a.heads) * D, static_cast<long long>(B) * a.vbt_stride, a.ldvbt, C::kDpad))
+      return cudaErrorInvalidValue;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  AttnKernelArgs ka;
+  ka.out = a.out;
+  ka.ldo = a.ldo;
+  ka.L = a.L;
+  ka.Lb = a.Lb;
+  ka.F = a.F > 0 ? a.F : 1;
+  ka.nf_nobank = a.nf_nobank;
+  ka.heads = a.heads;
+  ka.vt_stride = static_cast<int>(a.vt_stride);
+  ka.vbt_stride = static_cast<int>(a.vbt_stride);
+  ka.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
+  dim3 grid((a.L + QT - 1) / QT, a.heads, a.NF);
+  attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const AttnArgs& a, int /*num_sms*/, cudaStream_t stream) {
+  switch (a.d) {
+    case 8: return launch_attn_t<8>(a, stream);
+    case 16: return launch_attn_t<16>(a, stream);
+    case 32: return launch_attn_t<32>(a, stream);
+    case 40: return launch_attn_t<40>(a, stream);
+    case 80: return launch_attn_t<80>(a, stream);
+    case 160: return launch_attn_t<160>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace hv

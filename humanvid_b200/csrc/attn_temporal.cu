@@ -1,0 +1,177 @@
+// Attention over the frame axis (AnimateDiff motion module, reference src/models/motion_module.py:351-388 and
+// src/cameractrl/motion_module.py:323-388): for every (batch item, pixel, head) a softmax(q k^T / sqrt(d)) v with
+// F <= 32 frames.  The reference materialises "(b f) d c -> (b d) f c" transposes around SDPA; here the frame axis is
+// simply the strided axis of the channels-last token matrix, so nothing is transposed in memory.
+//
+// One warp per (b, pixel, head).  Q K^T and P V run on mma.sync.m16n8k16 register fragments (problems are 24x24xd:
+// far too small for a tcgen05 tile; the op is bound by HBM traffic of q,k,v,o, ~0.2% of the step's FLOPs), the
+// softmax row max / row sum are warp-shuffle reductions over the 4 lanes that share a row.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hv {
+
+namespace {
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t ldg_h2(const __half* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2h(__half a, __half b) {
+  __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// QKV: [B*F*HW][3*C] rows (b, f, p); q at column h*D, k at C + h*D, v at 2C + h*D.
+template <int D>
+__global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B,
+                                                           int F, int HW, int heads, float scale_log2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long prob = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const long long nprob = static_cast<long long>(B) * HW * heads;
+  if (prob >= nprob) return;
+  const int h = static_cast<int>(prob % heads);
+  const long long bp = prob / heads;
+  const int p = static_cast<int>(bp % HW);
+  const int b = static_cast<int>(bp / HW);
+  const int C = heads * D;
+  const long long ld = 3LL * C;
+  const long long fstride = static_cast<long long>(HW) * ld;  // elements between consecutive frames of one pixel
+  const __half* qb = qkv + (static_cast<long long>(b) * F * HW + p) * ld + h * D;
+  const __half* kb = qb + C;
+  const __half* vb = qb + 2 * C;
+
+  constexpr int KS = (D + 15) / 16;  // k16 steps of Q K^T
+  // ---- S = Q K^T : 2 m-tiles (frames 0..31) x 4 n-tiles (keys 0..31)
+  float s[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.f;
+
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int c_lo = ks * 16 + 2 * t, c_hi = c_lo + 8;
+    const bool lo_ok = ks * 16 < D, hi_ok = ks * 16 + 8 < D;
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      a[mt][0] = (lo_ok && r0 < F) ? ldg_h2(qb + r0 * fstride + c_lo) : 0u;
+      a[mt][1] = (lo_ok && r1 < F) ? ldg_h2(qb + r1 * fstride + c_lo) : 0u;
+      a[mt][2] = (hi_ok && r0 < F) ? ldg_h2(qb + r0 * fstride + c_hi) : 0u;
+      a[mt][3] = (hi_ok && r1 < F) ? ldg_h2(qb + r1 * fstride + c_hi) : 0u;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int j = nt * 8 + g;
+      const uint32_t b0 = (lo_ok && j < F) ? ldg_h2(kb + j * fstride + c_lo) : 0u;
+      const uint32_t b1 = (hi_ok && j < F) ? ldg_h2(kb + j * fstride + c_hi) : 0u;
+      mma16816(s[0][nt], a[0], b0, b1);
+      mma16816(s[1][nt], a[1], b0, b1);
+    }
+  }
+
+  // ---- softmax over keys (columns); rows g / g+8 of each m-tile; quad (t) shares a row
+  uint32_t pa[2][2][4];  // P as A fragments: [m-tile][k16 step over keys][4]
+  float inv_sum[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // half 0: row g (regs 0,1), half 1: row g+8 (regs 2,3)
+      float m = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j0 = nt * 8 + 2 * t;
+        if (j0 < F) m = fmaxf(m, s[mt][nt][half * 2]);
+        if (j0 + 1 < F) m = fmaxf(m, s[mt][nt][half * 2 + 1]);
+      }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j0 = nt * 8 + 2 * t;
+        float e0 = j0 < F ? exp2f((s[mt][nt][half * 2] - m) * scale_log2) : 0.f;
+        float e1 = j0 + 1 < F ? exp2f((s[mt][nt][half * 2 + 1] - m) * scale_log2) : 0.f;
+        sum += e0 + e1;
+        s[mt][nt][half * 2] = e0;
+        s[mt][nt][half * 2 + 1] = e1;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv_sum[mt][half] = 1.f / sum;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      pa[mt][kk][0] = pack2(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+      pa[mt][kk][1] = pack2(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+      pa[mt][kk][2] = pack2(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+      pa[mt][kk][3] = pack2(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+    }
+  }
+
+  // ---- O = P V, one n8 tile of the head dim at a time
+  __half* ob = out + (static_cast<long long>(b) * F * HW + p) * C + h * D;
+  const long long ostride = static_cast<long long>(HW) * C;
+  const __half zero = __float2half(0.f);
+#pragma unroll 1
+  for (int nt = 0; nt < D / 8; ++nt) {
+    const int c = nt * 8 + g;
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int j = kk * 16 + 2 * t;
+      const __half v00 = j < F ? __ldg(vb + j * fstride + c) : zero;
+      const __half v01 = j + 1 < F ? __ldg(vb + (j + 1) * fstride + c) : zero;
+      const __half v10 = j + 8 < F ? __ldg(vb + (j + 8) * fstride + c) : zero;
+      const __half v11 = j + 9 < F ? __ldg(vb + (j + 9) * fstride + c) : zero;
+      const uint32_t b0 = pack2h(v00, v01), b1 = pack2h(v10, v11);
+      mma16816(o[0], pa[0][kk], b0, b1);
+      mma16816(o[1], pa[1][kk], b0, b1);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      const int col = nt * 8 + 2 * t;
+      if (r0 < F)
+        *reinterpret_cast<__half2*>(ob + r0 * ostride + col) = __floats2half2_rn(o[mt][0] * inv_sum[mt][0], o[mt][1] * inv_sum[mt][0]);
+      if (r1 < F)
+        *reinterpret_cast<__half2*>(ob + r1 * ostride + col) = __floats2half2_rn(o[mt][2] * inv_sum[mt][1], o[mt][3] * inv_sum[mt][1]);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_temporal_attention(const __half* qkv, __half* out, int B, int F, int HW, int heads, int d, cudaStream_t stream) {
+  if (F < 1 || F > 32) return cudaErrorInvalidValue;
+  const long long nprob = static_cast<long long>(B) * HW * heads;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((nprob + wpb - 1) / wpb);
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(d));
+  switch (d) {
+    case 40: temporal_attn_kernel<40><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    case 80: temporal_attn_kernel<80><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    case 160: temporal_attn_kernel<160><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    case 32: temporal_attn_kernel<32><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    case 16: temporal_attn_kernel<16><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    case 8: temporal_attn_kernel<8><<<grid, wpb * 32, 0, stream>>>(qkv, out, B, F, HW, heads, scale_log2); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace hv

@@ -1,0 +1,364 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M, N] = A[M, K] * B[N, K]^T, fp16 operands, fp32 accumulation in TMEM, fused epilogue, fp16 output.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  : cp.async.bulk.tensor loads of the A tile (128 rows x 64 k) and the B tile
+//                               (BLOCK_N rows x 64 k) into a ring of 128B-swizzled shared-memory stages
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), accumulators
+//                               double-buffered in TMEM (2 x BLOCK_N columns); owns TMEM alloc/dealloc
+//   warps 2..5  epilogue      : tcgen05.ld of the accumulator (one output row per thread), bias / time-embedding
+//                               row vector / activation / GEGLU / residual, fp16 store
+// The A operand is addressed through TMA only, so a 3x3 convolution over a channels-last (N,H,W,C) tensor is the
+// same kernel: k-block kb = (tap, 64-channel block) and the tile of 128 output pixels is a (bn x bh x bw) box whose
+// input window is fetched with the box shifted by the tap offset; TMA's out-of-bounds zero fill is the padding.
+// Stride-2 convolutions view the same memory as (N, H/2, 2, W/2, 2*C) so each tap is again a dense box.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace hv {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int GEMM_THREADS = 192;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int kBTileBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = A_TILE_BYTES + kBTileBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+struct TileCoord {
+  int m0;          // linear: first row.   conv: unused
+  int n0, y0, x0;  // conv: first frame / output row / output col of the box
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmProblem& p, int m_blk) {
+  TileCoord t;
+  if (p.a_mode == A_LINEAR) {
+    t.m0 = m_blk * BLOCK_M;
+    t.n0 = t.y0 = t.x0 = 0;
+  } else {
+    int xb = m_blk % p.tiles_x;
+    int r = m_blk / p.tiles_x;
+    int yb = r % p.tiles_y;
+    int nb = r / p.tiles_y;
+    t.m0 = 0;
+    t.n0 = nb * p.bn;
+    t.y0 = yb * p.bh;
+    t.x0 = xb * p.bw;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void store8(__half* dst, const float* v) {
+  uint4 u;
+  u.x = pack_h2(v[0], v[1]);
+  u.y = pack_h2(v[2], v[3]);
+  u.z = pack_h2(v[4], v[5]);
+  u.w = pack_h2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void load8(const __half* src, float* v) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_b, const GemmProblem p, const GemmEpilogue e) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bar_empty = bar_full + C::kStages;
+  uint64_t* bar_tfull = bar_empty + C::kStages;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + BLOCK_M - 1) / BLOCK_M : p.tiles_n * p.tiles_y * p.tiles_x;
+  const int n_per_batch = p.b_batch ? (p.b_rows + BLOCK_N - 1) / BLOCK_N : 0;
+  const int n_tiles = p.b_batch ? p.b_batch * n_per_batch : (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int nkb = p.num_k_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_tfull[s], 1);
+      mbar_init(&bar_tempty[s], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const TileCoord tc = tile_coord(p, m_blk);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&bar_full[stage], C::kStageBytes);
+          if (p.a_mode == A_LINEAR) {
+            if (p.k_split == 0 || kb < p.k_split)
+              tma_load_2d(sa, &map_a0, &bar_full[stage], kb * BLOCK_K, tc.m0);
+            else
+              tma_load_2d(sa, &map_a1, &bar_full[stage], (kb - p.k_split) * BLOCK_K, tc.m0);
+          } else {
+            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            if (p.a_mode == A_CONV3X3) {
+              tma_load_4d(sa, &map_a0, &bar_full[stage], cb * BLOCK_K, tc.x0 + dx - 1, tc.y0 + dy - 1, tc.n0);
+            } else {  // stride 2: memory viewed as (N, H/2, 2, W/2, 2C); input row 2*yo+dy-1, col 2*xo+dx-1
+              const int ph = dy == 1 ? 0 : 1, pw = dx == 1 ? 0 : 1;
+              tma_load_5d(sa, &map_a0, &bar_full[stage], pw * p.cin + cb * BLOCK_K, tc.x0 - (dx == 0 ? 1 : 0), ph,
+                          tc.y0 - (dy == 0 ? 1 : 0), tc.n0);
+            }
+          }
+          if (p.b_batch)
+            tma_load_3d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, (n_blk % n_per_batch) * BLOCK_N, n_blk / n_per_batch);
+          else
+            tma_load_2d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&bar_empty[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 1 output row / thread)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int r = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int kOutCols = BLOCK_N;  // per tile; geglu writes BLOCK_N/2
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const TileCoord tc = tile_coord(p, m_blk);
+      long long row;
+      bool row_ok;
+      if (p.a_mode == A_LINEAR) {
+        row = tc.m0 + r;
+        row_ok = row < p.M;
+      } else {
+        const int ix = r % p.bw, t2 = r / p.bw;
+        const int iy = t2 % p.bh, in = t2 / p.bh;
+        const int n = tc.n0 + in, y = tc.y0 + iy, x = tc.x0 + ix;
+        row_ok = n < p.NF && y < p.H && x < p.W;
+        row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      }
+      const __half* rv = nullptr;
+      if (e.rowvec != nullptr && row_ok) rv = e.rowvec + (row / e.rows_per_group) * e.rowvec_ld;
+      const __half* res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
+      __half* out = e.out + row * e.ldc;
+
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+      if (!e.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < kOutCols / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(t_acc + c * 32, raw);
+          tmem_ld_wait();
+          const int col0 = (p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + (n_blk % n_per_batch) * BLOCK_N : n_blk * BLOCK_N) + c * 32;
+          const int col_lim = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + ((p.b_rows + 7) & ~7) : e.n_valid;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= col_lim) break;
+            float v[8], t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]);
+            if (e.bias != nullptr) {
+              load8(e.bias + col, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
+            if (rv != nullptr) {
+              load8(rv + col, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+            }
+            if (e.act == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (e.act == ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
+            }
+            if (res != nullptr) {
+              load8(res + col, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = v[i] + t[i];
+            }
+            if (row_ok) store8(out + col, v);
+          }
+        }
+      } else {
+        // GEGLU: columns [0,128) of the tile are "hidden", [128,256) the matching "gate" rows of the packed weight.
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          uint32_t hraw[32], graw[32];
+          tmem_ld32(t_acc + c * 32, hraw);
+          tmem_ld32(t_acc + BLOCK_N / 2 + c * 32, graw);
+          tmem_ld_wait();
+          const int pcol0 = n_blk * BLOCK_N + c * 32;          // packed column of the hidden part
+          const int ocol0 = n_blk * (BLOCK_N / 2) + c * 32;    // output column
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ocol = ocol0 + g * 8;
+            if (ocol >= e.n_valid) break;
+            float hv[8], gv[8], t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              hv[i] = __uint_as_float(hraw[g * 8 + i]);
+              gv[i] = __uint_as_float(graw[g * 8 + i]);
+            }
+            if (e.bias != nullptr) {
+              load8(e.bias + pcol0 + g * 8, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hv[i] += t[i];
+              load8(e.bias + pcol0 + BLOCK_N / 2 + g * 8, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) gv[i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hv[i] = r16(hv[i]) * r16(gelu_erf_f(r16(gv[i])));
+            if (row_ok) store8(out + ocol, hv);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw) {
+  long long best = -1;
+  int b_n = 1, b_h = 1, b_w = 128;
+  for (int w = 128; w >= 1; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      int n = 128 / (w * h);
+      auto up = [](int a, int b) { return static_cast<long long>((a + b - 1) / b) * b; };
+      long long padded = up(NF, n) * up(H, h) * up(W, w);
+      if (best < 0 || padded < best) {  // ties keep the widest box along W (longest contiguous TMA rows)
+        best = padded;
+        b_n = n;
+        b_h = h;
+        b_w = w;
+      }
+    }
+  }
+  *bn = b_n;
+  *bh = b_h;
+  *bw = b_w;
+}
+
+cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
+                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream) {
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + BLOCK_M - 1) / BLOCK_M : p.tiles_n * p.tiles_y * p.tiles_x;
+  const int n_tiles = p.b_batch ? p.b_batch * ((p.b_rows + block_n - 1) / block_n) : (p.N + block_n - 1) / block_n;
+  const int tiles = m_tiles * n_tiles;
+  if (tiles <= 0 || p.num_k_blocks <= 0) return cudaErrorInvalidValue;
+  if (p.b_batch && (e.bias || e.rowvec || e.residual || e.geglu || (p.b_out_stride % 8))) return cudaErrorInvalidValue;
+  if (e.geglu && block_n != 256) return cudaErrorInvalidValue;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  cudaError_t err;
+  if (block_n == 256) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      err = cudaFuncSetAttribute(gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes);
+      if (err != cudaSuccess) return err;
+      attr_set = true;
+    }
+    gemm_kernel<256><<<grid, GEMM_THREADS, Cfg<256>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  } else if (block_n == 128) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      err = cudaFuncSetAttribute(gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes);
+      if (err != cudaSuccess) return err;
+      attr_set = true;
+    }
+    gemm_kernel<128><<<grid, GEMM_THREADS, Cfg<128>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace hv

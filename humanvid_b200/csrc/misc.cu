@@ -1,0 +1,306 @@
+// Glue kernels of the denoising path: layout changes at the (B,C,F,H,W) boundary, nearest upsampling, the tiny
+// linears of the time embedding / cross-attention collapse, small-channel direct convolutions (conv_in, PoseGuider),
+// weight packing, and a slow CUDA-core GEMM used only to localise faults in tests.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace hv {
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(long long n, int num_sms) {
+  long long b = (n + kThreads - 1) / kThreads;
+  long long cap = static_cast<long long>(num_sms) * 32;
+  return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// (B, C, F, H, W) [fp16 or fp32] -> (B*F, H, W, C) fp16.  Tiled transpose of the (C, HW) plane of each (b, f).
+template <typename T>
+__global__ void ncfhw_to_nhwc_kernel(const T* __restrict__ x, __half* __restrict__ out, int B, int C, int F, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;  // b*F + f
+  const int b = n / F, f = n % F;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = static_cast<float>(x[((static_cast<long long>(b) * C + c) * F + f) * HW + p]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) out[(static_cast<long long>(n) * HW + p) * C + c] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// (B*F, HW, ldx) fp16 (first C columns) -> (B, C, F, H, W) fp16
+__global__ void nhwc_to_ncfhw_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ out, int B, int C, int F, int HW) {
+  __shared__ __half tile[32][34];
+  const int n = blockIdx.z;
+  const int b = n / F, f = n % F;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = x[(static_cast<long long>(n) * HW + p) * ldx + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[((static_cast<long long>(b) * C + c) * F + f) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long total, int H, int W, int vecs) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int xo = static_cast<int>(r % (2 * W));
+    r /= 2 * W;
+    const int yo = static_cast<int>(r % (2 * H));
+    const long long n = r / (2 * H);
+    out[i] = __ldg(&x[((n * H + (yo >> 1)) * W + (xo >> 1)) * vecs + v]);
+  }
+}
+
+__global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ out, long long n2) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float2 fa = __half22float2(a[i]), fb = __half22float2(b[i]);
+    out[i] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+  }
+}
+
+// PixelUnshuffle(r) of (B, C, F, H, W) fp16 -> channels-last (B*F, H/r, W/r, C*r*r), channel = c*r*r + dy*r + dx
+__global__ void pixel_unshuffle_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long total, int B, int C, int F,
+                                       int H, int W, int r) {
+  const int Ho = H / r, Wo = W / r, Co = C * r * r;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Co);
+    long long t = i / Co;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const int b = static_cast<int>(n / F), f = static_cast<int>(n % F);
+    const int c = co / (r * r), dy = (co / r) % r, dx = co % r;
+    out[i] = x[(((static_cast<long long>(b) * C + c) * F + f) * H + (yo * r + dy)) * W + (xo * r + dx)];
+  }
+}
+
+// y[m][n] = r16( sum_k act(x[m][k]) * w[n][k] + bias[n] ); one warp per output element (M is tiny).
+__global__ void small_linear_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                                    __half* __restrict__ out, int M, int N, int K, int act_in) {
+  const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(wid / N), n = static_cast<int>(wid % N);
+  float acc = 0.f;
+  for (int k = lane * 2; k < K; k += 64) {
+    float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + static_cast<long long>(m) * K + k));
+    float2 wv = __half22float2(*reinterpret_cast<const __half2*>(w + static_cast<long long>(n) * K + k));
+    if (act_in == 2) {
+      xv.x = r16(silu_f(xv.x));
+      xv.y = r16(silu_f(xv.y));
+    }
+    acc += xv.x * wv.x + xv.y * wv.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[static_cast<long long>(m) * N + n] = __float2half_rn(acc + (bias ? __half2float(bias[n]) : 0.f));
+}
+
+__global__ void timestep_embedding_kernel(float t, __half* __restrict__ out, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, j = i % half;
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(j) / static_cast<float>(half));
+  const float arg = t * freq;
+  out[b * dim + j] = __float2half_rn(cosf(arg));
+  out[b * dim + half + j] = __float2half_rn(sinf(arg));
+}
+
+// Direct 3x3 conv for small channel counts: one thread per (pixel, 8 output channels).  X (NF,H,W,Cin) channels-last,
+// W (Cout, Cin, 3, 3).  fp32 accumulate; optional add (same shape as out) applied after bias (+act).
+__global__ void conv3x3_direct_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                                      __half* __restrict__ out, long long total, int H, int W, int Cin, int Cout, int stride,
+                                      int act, const __half* __restrict__ add, int ldo) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int cgroups = (Cout + 7) / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cgroups);
+    long long t = i / cgroups;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yi = yo * stride + ky - 1;
+      if (yi < 0 || yi >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xi = xo * stride + kx - 1;
+        if (xi < 0 || xi >= W) continue;
+        const __half* xp = x + ((n * H + yi) * W + xi) * Cin;
+        for (int c = 0; c < Cin; ++c) {
+          const float xv = __half2float(__ldg(xp + c));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int co = cg * 8 + j;
+            if (co < Cout) acc[j] += xv * __half2float(__ldg(w + ((static_cast<long long>(co) * Cin + c) * 3 + ky) * 3 + kx));
+          }
+        }
+      }
+    }
+    const long long obase = ((n * Ho + yo) * Wo + xo) * ldo;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = cg * 8 + j;
+      if (co < Cout) {
+        float v = r16(acc[j] + (bias ? __half2float(bias[co]) : 0.f));
+        if (act == 2) v = r16(silu_f(v));
+        else if (act == 1) v = fmaxf(v, 0.f);
+        if (add) v = v + __half2float(add[obase + co]);
+        out[obase + co] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight packing
+template <typename T>
+__global__ void pack_conv3x3_kernel(const T* __restrict__ w, __half* __restrict__ out, long long total, int Cout, int Cin, int CinPad) {
+  // out[co][tap*CinPad + c] = w[co][c][tap]; zero for padded output rows / input channels
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CinPad);
+    long long t = i / CinPad;
+    const int tap = static_cast<int>(t % 9);
+    const long long co = t / 9;
+    out[i] = (co < Cout && c < Cin) ? __float2half_rn(static_cast<float>(w[(co * Cin + c) * 9 + tap])) : __float2half_rn(0.f);
+  }
+}
+
+// rows: [hidden 0..R/2) | gate R/2..R) -> blocks of 256: [128 hidden | 128 gate]
+__global__ void pack_geglu_kernel(const __half* __restrict__ w, __half* __restrict__ out, long long total, int rows, int K) {
+  const int half_rows = rows / 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int prow = static_cast<int>(i / K);
+    const int blk = prow / 256, within = prow % 256;
+    const int src = within < 128 ? blk * 128 + within : half_rows + blk * 128 + (within - 128);
+    out[i] = w[static_cast<long long>(src) * K + k];
+  }
+}
+
+__global__ void pack_heads_kernel(const __half* __restrict__ w, __half* __restrict__ out, long long total, int d, int dpad, int K) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int prow = static_cast<int>(i / K);
+    const int h = prow / dpad, j = prow % dpad;
+    out[i] = j < d ? w[(static_cast<long long>(h) * d + j) * K + k] : __float2half_rn(0.f);
+  }
+}
+
+__global__ void dbg_gemm_kernel(const __half* __restrict__ a, long long lda, const __half* __restrict__ w, float* __restrict__ out, int M,
+                                int N, int K) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __half2float(a[m * lda + k]) * __half2float(w[static_cast<long long>(n) * K + k]);
+  out[i] = acc;
+}
+
+}  // namespace
+
+#define HV_LAUNCH_CHECK() return cudaGetLastError()
+
+cudaError_t launch_ncfhw_to_nhwc(const void* x, __half* out, int B, int C, int F, int H, int W, int src_fp32, cudaStream_t s) {
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B * F), block(32, 8);
+  if (src_fp32)
+    ncfhw_to_nhwc_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), out, B, C, F, HW);
+  else
+    ncfhw_to_nhwc_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), out, B, C, F, HW);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_nhwc_to_ncfhw(const __half* x, int ldx, __half* out, int B, int C, int F, int H, int W, cudaStream_t s) {
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B * F), block(32, 8);
+  nhwc_to_ncfhw_kernel<<<grid, block, 0, s>>>(x, ldx, out, B, C, F, HW);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_upsample2x(const __half* x, __half* out, long long NF, int H, int W, int C, int num_sms, cudaStream_t s) {
+  const int vecs = C / 8;
+  const long long total = NF * 4LL * H * W * vecs;
+  upsample2x_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), total, H, W, vecs);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_add(const __half* a, const __half* b, __half* out, long long n, int num_sms, cudaStream_t s) {
+  add_kernel<<<blocks_for(n / 2, num_sms), kThreads, 0, s>>>(reinterpret_cast<const __half2*>(a), reinterpret_cast<const __half2*>(b),
+                                                             reinterpret_cast<__half2*>(out), n / 2);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_pixel_unshuffle(const __half* x, __half* out, int B, int C, int F, int H, int W, int r, int num_sms, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * F * C * H * W;
+  pixel_unshuffle_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(x, out, total, B, C, F, H, W, r);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_small_linear(const __half* x, const __half* w, const __half* bias, __half* out, int M, int N, int K, int act_in,
+                                cudaStream_t s) {
+  const long long warps = static_cast<long long>(M) * N;
+  small_linear_kernel<<<static_cast<unsigned>((warps * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(x, w, bias, out, M, N, K, act_in);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_timestep_embedding(long long timestep, __half* out, int B, int dim, cudaStream_t s) {
+  const int n = B * dim / 2;
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<float>(timestep), out, B, dim);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_conv3x3_direct(const __half* x, const __half* w, const __half* bias, __half* out, long long NF, int H, int W, int Cin,
+                                  int Cout, int stride, int act, const __half* add, int num_sms, cudaStream_t s) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = NF * Ho * Wo * ((Cout + 7) / 8);
+  conv3x3_direct_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(x, w, bias, out, total, H, W, Cin, Cout, stride, act, add, Cout);
+  HV_LAUNCH_CHECK();
+}
+// same, writing into a channel-padded buffer (row stride ldo >= Cout; the pad channels must already be zero)
+cudaError_t launch_conv3x3_direct_padded(const __half* x, const __half* w, const __half* bias, __half* out, long long NF, int H, int W,
+                                         int Cin, int Cout, int ldo, int act, int num_sms, cudaStream_t s) {
+  const long long total = NF * H * W * ((Cout + 7) / 8);
+  conv3x3_direct_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(x, w, bias, out, total, H, W, Cin, Cout, 1, act, nullptr, ldo);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_pack_conv3x3(const __half* w, __half* out, int Cout, int Cin, int Cout_pad, int Cin_pad, int num_sms, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout_pad) * 9 * Cin_pad;
+  pack_conv3x3_kernel<__half><<<blocks_for(total, num_sms), kThreads, 0, s>>>(w, out, total, Cout, Cin, Cin_pad);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_pack_geglu(const __half* w, __half* out, int rows, int K, int num_sms, cudaStream_t s) {
+  const long long total = static_cast<long long>(rows) * K;
+  pack_geglu_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(w, out, total, rows, K);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_pack_heads(const __half* w, __half* out, int heads, int d, int dpad, int K, int num_sms, cudaStream_t s) {
+  const long long total = static_cast<long long>(heads) * dpad * K;
+  pack_heads_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(w, out, total, d, dpad, K);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_dbg_gemm(const __half* a, long long lda, const __half* w, float* out, int M, int N, int K, cudaStream_t s) {
+  const long long total = static_cast<long long>(M) * N;
+  dbg_gemm_kernel<<<static_cast<unsigned>((total + kThreads - 1) / kThreads), kThreads, 0, s>>>(a, lda, w, out, M, N, K);
+  HV_LAUNCH_CHECK();
+}
+
+}  // namespace hv

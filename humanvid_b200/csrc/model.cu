@@ -1,0 +1,972 @@
+// Network runtime behind include/hv_b200.h: weight ingestion under the reference's state_dict keys, packing into
+// kernel layouts, a stack-allocated activation workspace, and the three forwards (UNet3DConditionModel, PoseGuider,
+// CameraPoseEncoder) expressed as sequences of the operators in ops.h / kernels.h.
+//
+// Activations are channels-last fp16 (N = B*F frames, H, W, C) == a [tokens][C] matrix, so the reference's
+// "b c f h w -> (b f) c h w", "(bf) c h w -> (bf) (hw) c" and "(b f) d c -> (b d) f c" rearranges never touch memory:
+// spatial tokens are rows, frames of one pixel are rows HW apart.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hv_b200.h"
+#include "gemm.cuh"
+#include "kernels.h"
+#include "ops.h"
+#include "tma.h"
+
+namespace hv {
+
+struct Err {
+  int code;
+  std::string msg;
+};
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Err{code, buf};
+}
+static void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) fail(HV_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+static void ckop(int status, const char* what) {
+  if (status != HV_OK) fail(status, "%s: %s", what, last_error());
+}
+static inline int64_t rup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------ tensors / weights
+struct Raw {  // one state_dict entry, fp16 on device
+  __half* p = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct Mat {  // packed [rows][cols] fp16
+  __half* p = nullptr;
+  int64_t rows = 0, cols = 0;
+};
+struct Norm {
+  __half* g = nullptr;
+  __half* b = nullptr;
+  int C = 0;
+  float eps = 1e-5f;
+};
+struct Lin {
+  Mat w;
+  __half* bias = nullptr;
+};
+struct Conv3 {       // implicit-GEMM packed 3x3 conv
+  Mat w;             // [cout_pad][9 * cin_pad]
+  __half* bias = nullptr;  // [cout_pad]
+  int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
+};
+struct ConvDirect {  // reference layout (Cout, Cin, 3, 3)
+  __half* w = nullptr;
+  __half* bias = nullptr;
+  int cin = 0, cout = 0;
+};
+
+struct Tens {  // channels-last activation
+  __half* p = nullptr;
+  int NF = 0, H = 0, W = 0, C = 0;
+  int64_t rows() const { return static_cast<int64_t>(NF) * H * W; }
+  int64_t numel() const { return rows() * C; }
+};
+
+struct ResnetW {
+  Norm n1, n2;
+  Conv3 c1, c2;
+  Lin temb;
+  bool has_sc = false;
+  Lin sc;
+  int cin = 0, cout = 0;
+};
+struct SpatialW {
+  Norm gn, ln1, ln3;
+  Lin proj_in, proj_out;
+  Mat wqk;   // [2*heads*dpad][C]  (q rows then k rows, each head zero-padded to dpad)
+  Mat wk;    // [heads*dpad][C]    view into wqk (bank keys)
+  Mat wv;    // [C][C]
+  Lin out1;
+  Lin v2, out2;  // cross-attention collapse: to_v (C x xdim), to_out
+  Lin ff1, ff2;  // ff1 geglu-packed
+  int C = 0, heads = 0, d = 0, dpad = 0;
+  // reference bank (B_ref, L, C)
+  __half* bank = nullptr;
+  int64_t bank_B = 0, bank_L = 0;
+  std::string name;
+};
+struct TAttnW {
+  Norm ln;
+  Mat wqkv;  // [3C][C]
+  Lin out;
+  __half* pe = nullptr;  // [max_len][C]
+  int max_len = 0;
+};
+struct MotionW {
+  Norm gn, ffn;
+  Lin proj_in, proj_out, ff1, ff2;
+  std::vector<TAttnW> attn;
+  int C = 0, heads = 0, d = 0;
+};
+struct CamResW {
+  Conv3 block1;
+  Lin block2;
+};
+
+// ------------------------------------------------------------------------------------------ workspace arena
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;  // measuring pass: hand out offsets only, launch nothing
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    if (!dry && off + bytes > cap) fail(HV_ERR_INVALID, "workspace too small: need > %zu bytes, have %zu", off + bytes, cap);
+    void* p = base + off;
+    off += bytes;
+    peak = std::max(peak, off);
+    return p;
+  }
+};
+struct Scope {
+  Arena& a;
+  size_t mark;
+  explicit Scope(Arena& ar) : a(ar), mark(ar.off) {}
+  ~Scope() { a.off = mark; }
+};
+
+}  // namespace hv
+
+using namespace hv;
+
+// ------------------------------------------------------------------------------------------ the model object
+struct hv_model {
+  hv_config cfg{};
+  std::string err;
+  std::unordered_map<std::string, Raw> raw;
+  std::vector<void*> owned;  // cudaMalloc'ed blocks (weights, banks)
+  bool finalized = false;
+  int sms = 0;
+  cudaStream_t st = nullptr;
+  Arena ar;
+  void* private_ws = nullptr;
+  size_t private_ws_bytes = 0;
+  int64_t launches = 0;
+
+  // ---- UNet
+  ConvDirect conv_in;
+  Lin te1, te2;
+  struct DownBlk { std::vector<ResnetW> res; std::vector<SpatialW> attn; std::vector<MotionW> mm; bool has_down = false; Conv3 down; };
+  struct UpBlk { std::vector<ResnetW> res; std::vector<SpatialW> attn; std::vector<MotionW> mm; bool has_up = false; Conv3 up; };
+  std::vector<DownBlk> down;
+  struct { std::vector<ResnetW> res; std::vector<SpatialW> attn; std::vector<MotionW> mm; } mid;
+  std::vector<UpBlk> up;
+  Norm norm_out;
+  Conv3 conv_out;
+  std::vector<SpatialW*> readers;  // reference-bank order
+  // ---- PoseGuider
+  ConvDirect pg_in;
+  std::vector<Conv3> pg_convs;  // blocks.0..5, conv_out
+  std::vector<int> pg_strides;
+  // ---- CameraPoseEncoder
+  Conv3 cam_in;
+  std::vector<CamResW> cam_res;
+  std::vector<MotionW> cam_att;  // reuse MotionW: attn[0] + ff (no gn / proj)
+  Lin cam_zero;
+
+  ~hv_model() {
+    for (void* p : owned) cudaFree(p);
+    if (private_ws) cudaFree(private_ws);
+  }
+
+  // ================================================================== weight helpers
+  __half* dmalloc(int64_t halves) {
+    void* p = nullptr;
+    ck(cudaMalloc(&p, static_cast<size_t>(halves) * 2), "cudaMalloc(weights)");
+    owned.push_back(p);
+    return static_cast<__half*>(p);
+  }
+  const Raw& get(const std::string& key) {
+    auto it = raw.find(key);
+    if (it == raw.end()) fail(HV_ERR_MISSING, "missing weight '%s'", key.c_str());
+    return it->second;
+  }
+  bool has(const std::string& key) const { return raw.count(key) != 0; }
+
+  __half* vec(const std::string& key, int64_t n, int64_t pad_to = 0) {
+    const Raw& r = get(key);
+    if (r.numel() != n) fail(HV_ERR_INVALID, "weight '%s' has %lld elements, expected %lld", key.c_str(), (long long)r.numel(), (long long)n);
+    if (pad_to <= n) return r.p;
+    __half* p = dmalloc(pad_to);
+    ck(cudaMemsetAsync(p, 0, pad_to * 2, st), "memset");
+    ck(cudaMemcpyAsync(p, r.p, n * 2, cudaMemcpyDeviceToDevice, st), "memcpy");
+    return p;
+  }
+  Norm norm(const std::string& pfx, int C, float eps) {
+    Norm n;
+    n.g = vec(pfx + ".weight", C);
+    n.b = vec(pfx + ".bias", C);
+    n.C = C;
+    n.eps = eps;
+    return n;
+  }
+  Mat mat(const std::string& key, int64_t rows, int64_t cols) {  // 2-D (or 4-D 1x1 conv) weight used as is
+    const Raw& r = get(key);
+    if (r.numel() != rows * cols) fail(HV_ERR_INVALID, "weight '%s': %lld elements, expected %lld x %lld", key.c_str(), (long long)r.numel(), (long long)rows, (long long)cols);
+    return Mat{r.p, rows, cols};
+  }
+  Lin lin(const std::string& pfx, int64_t out, int64_t in, bool bias = true) {
+    Lin l;
+    l.w = mat(pfx + ".weight", out, in);
+    if (bias) l.bias = vec(pfx + ".bias", out);
+    return l;
+  }
+  Conv3 conv3(const std::string& pfx, int cout, int cin, bool bias = true) {
+    const Raw& r = get(pfx + ".weight");
+    if (r.shape.size() != 4 || r.shape[0] != cout || r.shape[1] != cin || r.shape[2] != 3 || r.shape[3] != 3)
+      fail(HV_ERR_INVALID, "weight '%s.weight' is not (%d,%d,3,3)", pfx.c_str(), cout, cin);
+    Conv3 c;
+    c.cin = cin;
+    c.cout = cout;
+    c.cin_pad = static_cast<int>(rup(cin, 64));
+    c.cout_pad = cout % 64 == 0 ? cout : static_cast<int>(cout < 64 ? rup(cout, 8) : rup(cout, 64));
+    c.w.rows = c.cout_pad;
+    c.w.cols = 9LL * c.cin_pad;
+    c.w.p = dmalloc(c.w.rows * c.w.cols);
+    ck(launch_pack_conv3x3(r.p, c.w.p, cout, cin, c.cout_pad, c.cin_pad, sms, st), "pack conv3x3");
+    if (bias) c.bias = vec(pfx + ".bias", cout, c.cout_pad);
+    return c;
+  }
+  ConvDirect conv_direct(const std::string& pfx, int cout, int cin) {
+    ConvDirect c;
+    c.w = get(pfx + ".weight").p;
+    c.bias = vec(pfx + ".bias", cout);
+    c.cin = cin;
+    c.cout = cout;
+    return c;
+  }
+  Lin ff1_geglu(const std::string& pfx, int C) {  // net.0.proj: [8C][C] + bias -> 128-row hidden/gate interleave
+    const Raw& w = get(pfx + ".weight");
+    const Raw& b = get(pfx + ".bias");
+    if (w.numel() != 8LL * C * C || b.numel() != 8LL * C) fail(HV_ERR_INVALID, "'%s' is not a GEGLU proj of dim %d", pfx.c_str(), C);
+    if ((4 * C) % 128) fail(HV_ERR_INVALID, "GEGLU inner dim %d must be a multiple of 128", 4 * C);
+    Lin l;
+    l.w = Mat{dmalloc(8LL * C * C), 8LL * C, C};
+    ck(launch_pack_geglu(w.p, l.w.p, 8 * C, C, sms, st), "pack geglu");
+    l.bias = dmalloc(8LL * C);
+    ck(launch_pack_geglu(b.p, l.bias, 8 * C, 1, sms, st), "pack geglu bias");
+    return l;
+  }
+
+  ResnetW resnet(const std::string& pfx, int cin, int cout, int temb) {
+    ResnetW r;
+    r.cin = cin;
+    r.cout = cout;
+    r.n1 = norm(pfx + ".norm1", cin, 1e-5f);
+    r.c1 = conv3(pfx + ".conv1", cout, cin);
+    r.temb = lin(pfx + ".time_emb_proj", cout, temb);
+    r.n2 = norm(pfx + ".norm2", cout, 1e-5f);
+    r.c2 = conv3(pfx + ".conv2", cout, cout);
+    r.has_sc = cin != cout;
+    if (r.has_sc) r.sc = lin(pfx + ".conv_shortcut", cout, cin);
+    return r;
+  }
+  SpatialW spatial(const std::string& pfx, int C) {
+    SpatialW s;
+    s.name = pfx;
+    s.C = C;
+    s.heads = cfg.heads;
+    s.d = C / cfg.heads;
+    s.dpad = static_cast<int>(rup(s.d, 16));
+    if (s.d % 8) fail(HV_ERR_INVALID, "head dim %d (C=%d / %d heads) must be a multiple of 8", s.d, C, cfg.heads);
+    s.gn = norm(pfx + ".norm", C, 1e-6f);
+    s.proj_in = lin(pfx + ".proj_in", C, C);
+    s.proj_out = lin(pfx + ".proj_out", C, C);
+    const std::string b = pfx + ".transformer_blocks.0";
+    s.ln1 = norm(b + ".norm1", C, 1e-5f);
+    s.ln3 = norm(b + ".norm3", C, 1e-5f);
+    const int64_t hp = static_cast<int64_t>(s.heads) * s.dpad;
+    s.wqk = Mat{dmalloc(2 * hp * C), 2 * hp, C};
+    ck(launch_pack_heads(mat(b + ".attn1.to_q.weight", C, C).p, s.wqk.p, s.heads, s.d, s.dpad, C, sms, st), "pack q");
+    ck(launch_pack_heads(mat(b + ".attn1.to_k.weight", C, C).p, s.wqk.p + hp * C, s.heads, s.d, s.dpad, C, sms, st), "pack k");
+    s.wk = Mat{s.wqk.p + hp * C, hp, C};
+    s.wv = mat(b + ".attn1.to_v.weight", C, C);
+    s.out1 = lin(b + ".attn1.to_out.0", C, C);
+    s.v2 = lin(b + ".attn2.to_v", C, cfg.cross_attention_dim, false);
+    s.out2 = lin(b + ".attn2.to_out.0", C, C);
+    s.ff1 = ff1_geglu(b + ".ff.net.0.proj", C);
+    s.ff2 = lin(b + ".ff.net.2", C, 4 * C);
+    return s;
+  }
+  TAttnW tattn(const std::string& attn_pfx, const std::string& norm_pfx, int C, int max_len) {
+    TAttnW t;
+    t.ln = norm(norm_pfx, C, 1e-5f);
+    t.wqkv = Mat{dmalloc(3LL * C * C), 3LL * C, C};
+    const char* names[3] = {".to_q.weight", ".to_k.weight", ".to_v.weight"};
+    for (int i = 0; i < 3; ++i)
+      ck(cudaMemcpyAsync(t.wqkv.p + static_cast<int64_t>(i) * C * C, mat(attn_pfx + names[i], C, C).p, static_cast<size_t>(C) * C * 2,
+                         cudaMemcpyDeviceToDevice, st), "qkv concat");
+    t.out = lin(attn_pfx + ".to_out.0", C, C);
+    const Raw& pe = get(attn_pfx + ".pos_encoder.pe");
+    if (pe.numel() % C) fail(HV_ERR_INVALID, "'%s.pos_encoder.pe' width != %d", attn_pfx.c_str(), C);
+    t.pe = pe.p;
+    t.max_len = static_cast<int>(pe.numel() / C);
+    (void)max_len;
+    return t;
+  }
+  MotionW motion(const std::string& pfx, int C) {
+    MotionW m;
+    m.C = C;
+    m.heads = cfg.heads;
+    m.d = C / cfg.heads;
+    const std::string t = pfx + ".temporal_transformer";
+    m.gn = norm(t + ".norm", C, 1e-6f);
+    m.proj_in = lin(t + ".proj_in", C, C);
+    m.proj_out = lin(t + ".proj_out", C, C);
+    const std::string b = t + ".transformer_blocks.0";
+    for (int i = 0; i < 2; ++i)
+      m.attn.push_back(tattn(b + ".attention_blocks." + std::to_string(i), b + ".norms." + std::to_string(i), C, cfg.motion_max_len));
+    m.ffn = norm(b + ".ff_norm", C, 1e-5f);
+    m.ff1 = ff1_geglu(b + ".ff.net.0.proj", C);
+    m.ff2 = lin(b + ".ff.net.2", C, 4 * C);
+    return m;
+  }
+
+  void build_unet() {
+    const int* ch = cfg.block_out_channels;
+    const int temb = ch[0] * 4;
+    const bool mm = cfg.use_motion_module != 0;
+    conv_in = conv_direct("conv_in", ch[0], cfg.in_channels);
+    te1 = lin("time_embedding.linear_1", temb, ch[0]);
+    te2 = lin("time_embedding.linear_2", temb, temb);
+    int prev = ch[0];
+    down.resize(4);
+    for (int i = 0; i < 4; ++i) {
+      auto& d = down[i];
+      const std::string p = "down_blocks." + std::to_string(i);
+      for (int j = 0; j < 2; ++j) {
+        d.res.push_back(resnet(p + ".resnets." + std::to_string(j), j == 0 ? prev : ch[i], ch[i], temb));
+        if (i < 3) d.attn.push_back(spatial(p + ".attentions." + std::to_string(j), ch[i]));
+        if (mm) d.mm.push_back(motion(p + ".motion_modules." + std::to_string(j), ch[i]));
+      }
+      d.has_down = i < 3;
+      if (d.has_down) d.down = conv3(p + ".downsamplers.0.conv", ch[i], ch[i]);
+      prev = ch[i];
+    }
+    mid.res.push_back(resnet("mid_block.resnets.0", ch[3], ch[3], temb));
+    mid.res.push_back(resnet("mid_block.resnets.1", ch[3], ch[3], temb));
+    mid.attn.push_back(spatial("mid_block.attentions.0", ch[3]));
+    if (mm) mid.mm.push_back(motion("mid_block.motion_modules.0", ch[3]));
+    const int rev[4] = {ch[3], ch[2], ch[1], ch[0]};
+    up.resize(4);
+    prev = rev[0];
+    for (int i = 0; i < 4; ++i) {
+      auto& u = up[i];
+      const std::string p = "up_blocks." + std::to_string(i);
+      const int c = rev[i], cin = rev[std::min(i + 1, 3)];
+      for (int j = 0; j < 3; ++j) {
+        const int rin = (j == 0 ? prev : c) + (j == 2 ? cin : c);
+        u.res.push_back(resnet(p + ".resnets." + std::to_string(j), rin, c, temb));
+        if (i > 0) u.attn.push_back(spatial(p + ".attentions." + std::to_string(j), c));
+        if (mm) u.mm.push_back(motion(p + ".motion_modules." + std::to_string(j), c));
+      }
+      u.has_up = i < 3;
+      if (u.has_up) u.up = conv3(p + ".upsamplers.0.conv", c, c);
+      prev = c;
+    }
+    norm_out = norm("conv_norm_out", ch[0], 1e-5f);
+    conv_out = conv3("conv_out", cfg.out_channels, ch[0]);
+    // reader order: DFS(down_blocks, up_blocks, mid_block), stable sort by descending width
+    readers.clear();
+    for (auto& d : down) for (auto& a : d.attn) readers.push_back(&a);
+    for (auto& u : up) for (auto& a : u.attn) readers.push_back(&a);
+    for (auto& a : mid.attn) readers.push_back(&a);
+    std::stable_sort(readers.begin(), readers.end(), [](const SpatialW* x, const SpatialW* y) { return x->C > y->C; });
+  }
+
+  void build_pose_guider() {
+    const int* bc = cfg.pg_block_channels;
+    pg_in = conv_direct("conv_in", bc[0], cfg.pg_cond_channels);
+    pg_convs.clear();
+    pg_strides.clear();
+    for (int i = 0; i < 3; ++i) {
+      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i), bc[i], bc[i]));
+      pg_strides.push_back(1);
+      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i + 1), bc[i + 1], bc[i]));
+      pg_strides.push_back(2);
+    }
+    pg_convs.push_back(conv3("conv_out", cfg.pg_out_channels, bc[3]));
+    pg_strides.push_back(1);
+  }
+
+  void build_camera() {
+    const int C = cfg.cam_channels;
+    cam_in = conv3("encoder_conv_in", C, cfg.cam_cin);
+    for (int j = 0; j < cfg.cam_nums_rb; ++j) {
+      const std::string p = "encoder_down_conv_blocks.0." + std::to_string(j);
+      CamResW r;
+      r.block1 = conv3(p + ".block1", C, C);
+      r.block2 = lin(p + ".block2", C, C);
+      cam_res.push_back(r);
+      const std::string a = "encoder_down_attention_blocks.0." + std::to_string(j);
+      MotionW m;
+      m.C = C;
+      m.heads = cfg.cam_heads;
+      m.d = C / cfg.cam_heads;
+      m.attn.push_back(tattn(a + ".attention_blocks.0", a + ".norms.0", C, cfg.cam_max_len));
+      m.ffn = norm(a + ".ff_norm", C, 1e-5f);
+      m.ff1 = ff1_geglu(a + ".ff.net.0.proj", C);
+      m.ff2 = lin(a + ".ff.net.2", C, 4 * C);
+      cam_att.push_back(m);
+    }
+    cam_zero = lin("zero_conv_layers.0", C, C, false);
+  }
+
+  // ================================================================== op wrappers (no-ops while measuring)
+  Tens alloc_act(int NF, int H, int W, int C) {
+    Tens a;
+    a.NF = NF; a.H = H; a.W = W; a.C = C;
+    a.p = static_cast<__half*>(ar.alloc(static_cast<size_t>(a.numel()) * 2));
+    return a;
+  }
+  __half* alloc_h(int64_t n) { return static_cast<__half*>(ar.alloc(static_cast<size_t>(n) * 2)); }
+
+  Tens op_gn(const Tens& x, const Tens* x2, const Norm& n, bool silu) {
+    const int C2 = x2 ? x2->C : 0;
+    if (n.C != x.C + C2) fail(HV_ERR_INVALID, "groupnorm width %d != %d + %d", n.C, x.C, C2);
+    Tens out = alloc_act(x.NF, x.H, x.W, x.C + C2);
+    float* stats = static_cast<float*>(ar.alloc(sizeof(float) * 2 * x.NF * cfg.norm_groups));
+    if (ar.dry) return out;
+    launches += 3;
+    ck(launch_groupnorm(x.p, x.C, x2 ? x2->p : nullptr, C2, n.g, n.b, out.p, x.NF, x.H * x.W, cfg.norm_groups, n.eps, silu ? 1 : 0, stats, sms, st),
+       "groupnorm");
+    return out;
+  }
+  // out = LN(x (+ pre_add per batch item)) (+ pe per frame); returns the normalised tensor, x_new receives x + pre_add
+  Tens op_ln(const Tens& x, const Norm& n, const __half* pre_add, int64_t rows_per_b, Tens* x_new, const __half* pe, int F) {
+    Tens out = alloc_act(x.NF, x.H, x.W, x.C);
+    if (pre_add && x_new) *x_new = alloc_act(x.NF, x.H, x.W, x.C);
+    if (ar.dry) return out;
+    launches += 1;
+    ck(launch_layernorm(x.p, n.g, n.b, out.p, x.rows(), x.C, n.eps, pre_add, rows_per_b, (pre_add && x_new) ? x_new->p : nullptr, pe, x.H * x.W, F, st),
+       "layernorm");
+    return out;
+  }
+  void gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_t K1, const Mat& w, __half* out, int64_t ldc, int64_t M,
+            const hv_epilogue* ep) {
+    if (ar.dry) return;
+    launches += 1;
+    ckop(op_gemm(A, lda, A2, lda2, K1, w.p, out, ldc, M, w.rows, w.cols, ep, st), "gemm");
+  }
+  // y = x W^T + b (+ residual)
+  Tens op_linear(const Tens& x, const Lin& l, const Tens* residual, int act = HV_ACT_NONE, bool geglu = false) {
+    const int N = static_cast<int>(geglu ? l.w.rows / 2 : l.w.rows);
+    if (l.w.cols != x.C) fail(HV_ERR_INVALID, "linear: input width %d != weight cols %lld", x.C, (long long)l.w.cols);
+    Tens out = alloc_act(x.NF, x.H, x.W, N);
+    hv_epilogue ep{};
+    ep.bias = l.bias;
+    ep.act = act;
+    ep.geglu = geglu ? 1 : 0;
+    if (residual) { ep.residual = residual->p; ep.ldr = residual->C; }
+    gemm(x.p, x.C, nullptr, 0, 0, l.w, out.p, N, x.rows(), &ep);
+    return out;
+  }
+  Tens op_conv3(const Tens& x, const Conv3& c, int stride, const __half* rowvec, int64_t rows_per_group, int act, const Tens* residual) {
+    if (x.C != c.cin_pad) fail(HV_ERR_INVALID, "conv3x3: input has %d channels, weight packed for %d", x.C, c.cin_pad);
+    const int Ho = stride == 1 ? x.H : x.H / 2, Wo = stride == 1 ? x.W : x.W / 2;
+    Tens out = alloc_act(x.NF, Ho, Wo, c.cout_pad);
+    if (ar.dry) return out;
+    hv_epilogue ep{};
+    ep.bias = c.bias;
+    ep.rowvec = rowvec;
+    ep.rowvec_ld = c.cout_pad;
+    ep.rows_per_group = static_cast<int32_t>(rows_per_group);
+    ep.act = act;
+    if (residual) { ep.residual = residual->p; ep.ldr = residual->C; }
+    launches += 1;
+    ckop(op_conv3x3(x.p, c.w.p, out.p, c.cout_pad, x.NF, x.H, x.W, c.cin_pad, c.cout_pad, stride, &ep, st), "conv3x3");
+    return out;
+  }
+  __half* op_small_linear(const __half* x, const Lin& l, int M, int act_in) {
+    __half* out = alloc_h(static_cast<int64_t>(M) * l.w.rows);
+    if (ar.dry) return out;
+    launches += 1;
+    ck(launch_small_linear(x, l.w.p, l.bias, out, M, static_cast<int>(l.w.rows), static_cast<int>(l.w.cols), act_in, st), "small_linear");
+    return out;
+  }
+
+  // ================================================================== blocks
+  // ResnetBlock3D (resnet.py:215-245); x2 = skip tensor concatenated on the channel axis (never materialised raw)
+  Tens resnet_fwd(const ResnetW& r, const Tens& x, const Tens* x2, const __half* emb, int B, int F) {
+    Tens out;
+    {
+      const int Cin = x.C + (x2 ? x2->C : 0);
+      if (Cin != r.cin) fail(HV_ERR_INVALID, "resnet expects %d channels, got %d", r.cin, Cin);
+      out = alloc_act(x.NF, x.H, x.W, r.cout);
+    }
+    Scope s(ar);
+    __half* tproj = op_small_linear(emb, r.temb, B, HV_ACT_SILU);  // time_emb_proj(silu(emb)) : [B][cout]
+    Tens h = op_gn(x, x2, r.n1, true);
+    Tens h1 = op_conv3(h, r.c1, 1, tproj, static_cast<int64_t>(F) * x.H * x.W, HV_ACT_NONE, nullptr);
+    Tens h2 = op_gn(h1, nullptr, r.n2, true);
+    Tens res = x;
+    if (r.has_sc) {
+      res = alloc_act(x.NF, x.H, x.W, r.cout);
+      hv_epilogue ep{};
+      ep.bias = r.sc.bias;
+      gemm(x.p, x.C, x2 ? x2->p : nullptr, x2 ? x2->C : 0, x2 ? x.C : 0, r.sc.w, res.p, r.cout, x.rows(), &ep);
+    } else if (x2) {
+      fail(HV_ERR_INVALID, "resnet with concatenated input must have a shortcut conv");
+    }
+    // conv2 + bias, + residual, written straight into `out`
+    if (!ar.dry) {
+      hv_epilogue ep{};
+      ep.bias = r.c2.bias;
+      ep.residual = res.p;
+      ep.ldr = res.C;
+      launches += 1;
+      ckop(op_conv3x3(h2.p, r.c2.w.p, out.p, r.cout, x.NF, x.H, x.W, r.c2.cin_pad, r.c2.cout_pad, 1, &ep, st), "resnet conv2");
+    }
+    return out;
+  }
+
+  // Transformer3DModel + TemporalBasicTransformerBlock (+ reference-bank read hook)
+  Tens spatial_fwd(const SpatialW& w, const Tens& x, const __half* ehs, int B, int F, bool cfg_split) {
+    Tens out = alloc_act(x.NF, x.H, x.W, x.C);
+    Scope s(ar);
+    const int C = w.C, L = x.H * x.W;
+    const int64_t tokens = x.rows();
+    Tens hn = op_gn(x, nullptr, w.gn, false);
+    Tens t = op_linear(hn, w.proj_in, nullptr);
+    // ---- attn1
+    Tens t1 = alloc_act(x.NF, x.H, x.W, C);  // t after self-attention residual
+    {
+      Scope s2(ar);
+      Tens n1 = op_ln(t, w.ln1, nullptr, 1, nullptr, nullptr, 1);
+      const int64_t hp = static_cast<int64_t>(w.heads) * w.dpad;
+      __half* qk = alloc_h(tokens * 2 * hp);
+      gemm(n1.p, C, nullptr, 0, 0, w.wqk, qk, 2 * hp, tokens, nullptr);
+      const int64_t Lp = rup(L, 8), ldvt = static_cast<int64_t>(x.NF) * Lp;
+      __half* vt = alloc_h(static_cast<int64_t>(C) * ldvt);
+      // V^T[C][frame n: n*Lp + j] = Wv [C][C] * n1^T : weights are the "A" operand, activations the batched "B" operand
+      if (!ar.dry) {
+        launches += 1;
+        ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, C, x.NF, L, Lp, C, st), "V^T gemm");
+      }
+      const bool use_bank = w.bank != nullptr;
+      __half *kb = nullptr, *vbt = nullptr;
+      int64_t ldvbt = 0, Lbp = 0;
+      if (use_bank) {
+        if (w.bank_B != B) fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld, forward batch is %d", w.name.c_str(), (long long)w.bank_B, B);
+        const int64_t bt = w.bank_B * w.bank_L;
+        kb = alloc_h(bt * hp);
+        gemm(w.bank, C, nullptr, 0, 0, w.wk, kb, hp, bt, nullptr);
+        Lbp = rup(w.bank_L, 8);
+        ldvbt = w.bank_B * Lbp;
+        vbt = alloc_h(static_cast<int64_t>(C) * ldvbt);
+        if (!ar.dry) {
+          launches += 1;
+          ckop(op_gemm_batched_b(w.wv.p, C, w.bank, C, vbt, ldvbt, C, w.bank_B, w.bank_L, Lbp, C, st), "bank V^T gemm");
+        }
+      }
+      Tens o = alloc_act(x.NF, x.H, x.W, C);
+      if (!ar.dry) {
+        AttnArgs a{};
+        a.q = qk; a.k = qk + hp; a.vt = vt; a.out = o.p;
+        a.NF = x.NF; a.L = L; a.heads = w.heads; a.d = w.d; a.dpad = w.dpad;
+        a.ldq = 2 * hp; a.ldk = 2 * hp; a.ldvt = ldvt; a.ldo = C;
+        a.kb = kb; a.vbt = vbt; a.Lb = use_bank ? static_cast<int>(w.bank_L) : 0; a.ldkb = hp; a.ldvbt = ldvbt;
+        a.F = F; a.nf_nobank = cfg_split ? (B / 2) * F : 0;
+        a.vt_stride = Lp; a.vbt_stride = Lbp;
+        launches += 1;
+        cudaError_t e = launch_attention(a, sms, st);
+        if (e != cudaSuccess) fail(HV_ERR_CUDA, "attention (%s): %s %s", w.name.c_str(), cudaGetErrorString(e), tma_last_error());
+      }
+      hv_epilogue ep{};
+      ep.bias = w.out1.bias;
+      ep.residual = t.p;
+      ep.ldr = C;
+      gemm(o.p, C, nullptr, 0, 0, w.out1.w, t1.p, C, tokens, &ep);
+    }
+    // ---- attn2 with a single key: softmax == 1 -> out = to_out(to_v(ehs_b)) for every token of batch item b
+    __half* v2 = op_small_linear(ehs, w.v2, B, HV_ACT_NONE);
+    __half* ca = op_small_linear(v2, w.out2, B, HV_ACT_NONE);
+    Tens t2;
+    Tens n3 = op_ln(t1, w.ln3, ca, static_cast<int64_t>(F) * L, &t2, nullptr, 1);
+    // ---- feed-forward
+    Tens ffh = op_linear(n3, w.ff1, nullptr, HV_ACT_NONE, true);
+    Tens t3 = op_linear(ffh, w.ff2, &t2);
+    // ---- proj_out + residual
+    hv_epilogue ep{};
+    ep.bias = w.proj_out.bias;
+    ep.residual = x.p;
+    ep.ldr = x.C;
+    gemm(t3.p, C, nullptr, 0, 0, w.proj_out.w, out.p, C, tokens, &ep);
+    return out;
+  }
+
+  // one temporal attention sub-block: t = to_out(attn(LN(t) + pe)) + t
+  Tens tattn_fwd(const TAttnW& a, const Tens& t, int B, int F, int heads, int d) {
+    if (F > a.max_len) fail(HV_ERR_INVALID, "video_length %d exceeds temporal_position_encoding_max_len %d", F, a.max_len);
+    Tens out = alloc_act(t.NF, t.H, t.W, t.C);
+    Scope s(ar);
+    const int C = t.C;
+    Tens n = op_ln(t, a.ln, nullptr, 1, nullptr, a.pe, F);
+    __half* qkv = alloc_h(t.rows() * 3 * C);
+    gemm(n.p, C, nullptr, 0, 0, a.wqkv, qkv, 3 * C, t.rows(), nullptr);
+    Tens o = alloc_act(t.NF, t.H, t.W, C);
+    if (!ar.dry) {
+      launches += 1;
+      ck(launch_temporal_attention(qkv, o.p, B, F, t.H * t.W, heads, d, st), "temporal attention");
+    }
+    hv_epilogue ep{};
+    ep.bias = a.out.bias;
+    ep.residual = t.p;
+    ep.ldr = C;
+    gemm(o.p, C, nullptr, 0, 0, a.out.w, out.p, C, t.rows(), &ep);
+    return out;
+  }
+
+  // VanillaTemporalModule (motion_module.py:44-259)
+  Tens motion_fwd(const MotionW& m, const Tens& x, int B, int F) {
+    Tens out = alloc_act(x.NF, x.H, x.W, x.C);
+    Scope s(ar);
+    Tens hn = op_gn(x, nullptr, m.gn, false);
+    Tens t = op_linear(hn, m.proj_in, nullptr);
+    for (const auto& a : m.attn) t = tattn_fwd(a, t, B, F, m.heads, m.d);
+    Tens n = op_ln(t, m.ffn, nullptr, 1, nullptr, nullptr, 1);
+    Tens ffh = op_linear(n, m.ff1, nullptr, HV_ACT_NONE, true);
+    Tens t2 = op_linear(ffh, m.ff2, &t);
+    hv_epilogue ep{};
+    ep.bias = m.proj_out.bias;
+    ep.residual = x.p;
+    ep.ldr = x.C;
+    gemm(t2.p, x.C, nullptr, 0, 0, m.proj_out.w, out.p, x.C, x.rows(), &ep);
+    return out;
+  }
+
+  // ================================================================== forwards
+  void begin(void* ws, size_t ws_bytes, bool dry, cudaStream_t stream) {
+    st = stream;
+    ar.dry = dry;
+    ar.off = 0;
+    ar.peak = 0;
+    launches = 0;
+    if (dry) {
+      ar.base = nullptr;
+      ar.cap = 0;
+    } else {
+      ar.base = static_cast<uint8_t*>(ws);
+      ar.cap = ws_bytes;
+    }
+  }
+
+  void unet_forward(const __half* sample, int64_t timestep, const __half* ehs, const __half* pose, __half* outp, int B, int F, int H, int W,
+                    uint32_t flags) {
+    const int* ch = cfg.block_out_channels;
+    const int NF = B * F;
+    if ((H % 8) || (W % 8)) fail(HV_ERR_INVALID, "latent size %dx%d must be a multiple of 8 (three stride-2 levels)", H, W);
+    const bool cfg_split = (flags & HV_FLAG_CFG) != 0 && B >= 2 && B % 2 == 0;
+    // time embedding (unet_3d.py:446-467)
+    __half* tsin = alloc_h(static_cast<int64_t>(B) * ch[0]);
+    if (!ar.dry) { launches += 1; ck(launch_timestep_embedding(timestep, tsin, B, ch[0], st), "timestep embedding"); }
+    __half* e1 = op_small_linear(tsin, te1, B, HV_ACT_NONE);
+    __half* emb = op_small_linear(e1, te2, B, HV_ACT_SILU);
+    // conv_in (+ pose_cond_fea)
+    Tens x0 = alloc_act(NF, H, W, cfg.in_channels);
+    Tens pc = pose ? alloc_act(NF, H, W, ch[0]) : Tens{};
+    Tens h = alloc_act(NF, H, W, ch[0]);
+    if (!ar.dry) {
+      launches += 2 + (pose ? 1 : 0);
+      ck(launch_ncfhw_to_nhwc(sample, x0.p, B, cfg.in_channels, F, H, W, 0, st), "sample layout");
+      if (pose) ck(launch_ncfhw_to_nhwc(pose, pc.p, B, ch[0], F, H, W, 0, st), "pose layout");
+      ck(launch_conv3x3_direct(x0.p, conv_in.w, conv_in.bias, h.p, NF, H, W, conv_in.cin, conv_in.cout, 1, HV_ACT_NONE, pose ? pc.p : nullptr, sms, st),
+         "conv_in");
+    }
+    std::vector<Tens> skips{h};
+    for (size_t i = 0; i < down.size(); ++i) {
+      auto& d = down[i];
+      for (size_t j = 0; j < d.res.size(); ++j) {
+        h = resnet_fwd(d.res[j], h, nullptr, emb, B, F);
+        if (!d.attn.empty()) h = spatial_fwd(d.attn[j], h, ehs, B, F, cfg_split);
+        if (!d.mm.empty()) h = motion_fwd(d.mm[j], h, B, F);
+        skips.push_back(h);
+      }
+      if (d.has_down) {
+        h = op_conv3(h, d.down, 2, nullptr, 1, HV_ACT_NONE, nullptr);
+        skips.push_back(h);
+      }
+    }
+    h = resnet_fwd(mid.res[0], h, nullptr, emb, B, F);
+    h = spatial_fwd(mid.attn[0], h, ehs, B, F, cfg_split);
+    if (!mid.mm.empty()) h = motion_fwd(mid.mm[0], h, B, F);
+    h = resnet_fwd(mid.res[1], h, nullptr, emb, B, F);
+    for (size_t i = 0; i < up.size(); ++i) {
+      auto& u = up[i];
+      for (size_t j = 0; j < u.res.size(); ++j) {
+        Tens skip = skips.back();
+        skips.pop_back();
+        h = resnet_fwd(u.res[j], h, &skip, emb, B, F);
+        if (!u.attn.empty()) h = spatial_fwd(u.attn[j], h, ehs, B, F, cfg_split);
+        if (!u.mm.empty()) h = motion_fwd(u.mm[j], h, B, F);
+      }
+      if (u.has_up) {
+        Tens big = alloc_act(h.NF, 2 * h.H, 2 * h.W, h.C);
+        if (!ar.dry) { launches += 1; ck(launch_upsample2x(h.p, big.p, h.NF, h.H, h.W, h.C, sms, st), "upsample"); }
+        h = op_conv3(big, u.up, 1, nullptr, 1, HV_ACT_NONE, nullptr);
+      }
+    }
+    Tens hn = op_gn(h, nullptr, norm_out, true);
+    Tens y = op_conv3(hn, conv_out, 1, nullptr, 1, HV_ACT_NONE, nullptr);
+    if (!ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(y.p, y.C, outp, B, cfg.out_channels, F, H, W, st), "output layout"); }
+  }
+
+  void pose_guider_forward(const __half* cond, __half* outp, int B, int F, int H, int W) {
+    const int NF = B * F;
+    if ((H % 8) || (W % 8)) fail(HV_ERR_INVALID, "pose image %dx%d must be a multiple of 8", H, W);
+    Tens x0 = alloc_act(NF, H, W, cfg.pg_cond_channels);
+    Tens h = alloc_act(NF, H, W, pg_convs[0].cin_pad);
+    if (!ar.dry) {
+      launches += 3;
+      ck(launch_ncfhw_to_nhwc(cond, x0.p, B, cfg.pg_cond_channels, F, H, W, 0, st), "pose image layout");
+      ck(cudaMemsetAsync(h.p, 0, static_cast<size_t>(h.numel()) * 2, st), "memset");
+      ck(launch_conv3x3_direct_padded(x0.p, pg_in.w, pg_in.bias, h.p, NF, H, W, pg_in.cin, pg_in.cout, h.C, HV_ACT_SILU, sms, st), "pose conv_in");
+    }
+    for (size_t i = 0; i < pg_convs.size(); ++i) {
+      const bool last = i + 1 == pg_convs.size();
+      h = op_conv3(h, pg_convs[i], pg_strides[i], nullptr, 1, last ? HV_ACT_NONE : HV_ACT_SILU, nullptr);
+      // the next conv expects cin_pad channels: cout_pad of this conv equals it by construction (both round to 64)
+      if (!last && h.C != pg_convs[i + 1].cin_pad) fail(HV_ERR_INVALID, "pose guider channel padding mismatch at conv %zu", i);
+    }
+    if (!ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(h.p, h.C, outp, B, cfg.pg_out_channels, F, h.H, h.W, st), "pose output layout"); }
+  }
+
+  void camera_forward(const __half* plucker, __half* outp, int B, int F, int H, int W) {
+    const int r = cfg.cam_downscale, NF = B * F, C = cfg.cam_channels;
+    if ((H % r) || (W % r)) fail(HV_ERR_INVALID, "plucker map %dx%d must be a multiple of %d", H, W, r);
+    const int cin0 = cfg.cam_cin / (r * r);
+    Tens u = alloc_act(NF, H / r, W / r, cfg.cam_cin);
+    if (!ar.dry) { launches += 1; ck(launch_pixel_unshuffle(plucker, u.p, B, cin0, F, H, W, r, sms, st), "pixel unshuffle"); }
+    Tens x = op_conv3(u, cam_in, 1, nullptr, 1, HV_ACT_NONE, nullptr);
+    for (int j = 0; j < cfg.cam_nums_rb; ++j) {
+      // ResnetBlock (pose_adaptor.py:102-135, sk=True, ksize=1): x = block2(relu(block1(x))) + x
+      Tens h1 = op_conv3(x, cam_res[j].block1, 1, nullptr, 1, HV_ACT_RELU, nullptr);
+      x = op_linear(h1, cam_res[j].block2, &x);
+      // TemporalTransformerBlock over the frame axis
+      const MotionW& m = cam_att[j];
+      Tens t = tattn_fwd(m.attn[0], x, B, F, m.heads, m.d);
+      Tens n = op_ln(t, m.ffn, nullptr, 1, nullptr, nullptr, 1);
+      Tens ffh = op_linear(n, m.ff1, nullptr, HV_ACT_NONE, true);
+      x = op_linear(ffh, m.ff2, &t);
+    }
+    Tens z = op_linear(x, cam_zero, nullptr);
+    if (!ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(z.p, z.C, outp, NF, C, 1, z.H, z.W, st), "camera output layout"); }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ C ABI
+#define HV_GUARD(h, ...)                                  \
+  try {                                                   \
+    __VA_ARGS__;                                          \
+    return HV_OK;                                         \
+  } catch (const Err& e) {                                \
+    if (h) (h)->err = e.msg;                              \
+    set_error("%s", e.msg.c_str());                       \
+    return e.code;                                        \
+  } catch (const std::exception& e) {                     \
+    if (h) (h)->err = e.what();                           \
+    set_error("%s", e.what());                            \
+    return HV_ERR_INVALID;                                \
+  }
+
+static void* get_ws(hv_model* m, void* ws, size_t ws_bytes, size_t need, size_t* have) {
+  if (ws) {
+    *have = ws_bytes;
+    return ws;
+  }
+  if (m->private_ws_bytes < need) {
+    if (m->private_ws) cudaFree(m->private_ws);
+    m->private_ws = nullptr;
+    m->private_ws_bytes = 0;
+    ck(cudaMalloc(&m->private_ws, need), "cudaMalloc(workspace)");
+    m->private_ws_bytes = need;
+  }
+  *have = m->private_ws_bytes;
+  return m->private_ws;
+}
+
+extern "C" {
+
+int hv_create(const hv_config* cfg, hv_handle* out) {
+  if (!cfg || !out) return HV_ERR_INVALID;
+  hv_model* m = nullptr;
+  try {
+    const int sms = device_sms();
+    if (!sms) fail(HV_ERR_CUDA, "%s", last_error());
+    m = new hv_model();
+    m->cfg = *cfg;
+    m->sms = sms;
+    if (cfg->kind < 0 || cfg->kind > 2) fail(HV_ERR_INVALID, "unknown kind %d", cfg->kind);
+    *out = m;
+    return HV_OK;
+  } catch (const Err& e) {
+    set_error("%s", e.msg.c_str());
+    delete m;
+    return e.code;
+  }
+}
+
+void hv_destroy(hv_handle h) { delete h; }
+const char* hv_last_error(hv_handle h) { return h ? h->err.c_str() : last_error(); }
+int64_t hv_last_launch_count(hv_handle h) { return h ? h->launches : 0; }
+
+__global__ void cast_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __float2half_rn(x[i]);
+}
+
+int hv_set_weight(hv_handle h, const char* key, const void* dev_ptr, const int64_t* shape, int32_t ndim, int32_t dtype, hv_stream_t stream) {
+  if (!h || !key || !dev_ptr || ndim < 0 || ndim > 8) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (h->finalized) fail(HV_ERR_STATE, "hv_set_weight after hv_finalize");
+    Raw r;
+    r.shape.assign(shape, shape + ndim);
+    const int64_t n = r.numel();
+    if (n <= 0) fail(HV_ERR_INVALID, "weight '%s' is empty", key);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* p = nullptr;
+    ck(cudaMalloc(&p, static_cast<size_t>(rup(n, 8)) * 2), "cudaMalloc(weight)");
+    h->owned.push_back(p);
+    r.p = static_cast<__half*>(p);
+    if (dtype == HV_F16) {
+      ck(cudaMemcpyAsync(r.p, dev_ptr, static_cast<size_t>(n) * 2, cudaMemcpyDeviceToDevice, st), "weight copy");
+    } else if (dtype == HV_F32) {
+      long long blocks = std::min<long long>((n + 255) / 256, 4096);
+      cast_f32_to_f16<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const float*>(dev_ptr), r.p, n);
+      ck(cudaGetLastError(), "weight cast");
+    } else {
+      fail(HV_ERR_INVALID, "weight '%s': unsupported dtype %d", key, dtype);
+    }
+    h->raw[key] = r;
+  });
+}
+
+int hv_finalize(hv_handle h, hv_stream_t stream) {
+  if (!h) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (h->finalized) return HV_OK;
+    h->st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.kind == HV_KIND_UNET3D) h->build_unet();
+    else if (h->cfg.kind == HV_KIND_POSE_GUIDER) h->build_pose_guider();
+    else h->build_camera();
+    h->finalized = true;
+  });
+}
+
+int hv_num_ref_blocks(hv_handle h) { return (h && h->finalized) ? static_cast<int>(h->readers.size()) : 0; }
+int hv_ref_block_dim(hv_handle h, int32_t i) {
+  return (h && h->finalized && i >= 0 && i < static_cast<int>(h->readers.size())) ? h->readers[i]->C : 0;
+}
+
+int hv_set_ref_bank(hv_handle h, int32_t idx, const void* dev_ptr, int64_t B_ref, int64_t L, int64_t C, hv_stream_t stream) {
+  if (!h) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized) fail(HV_ERR_STATE, "hv_set_ref_bank before hv_finalize");
+    if (idx < 0 || idx >= static_cast<int>(h->readers.size())) fail(HV_ERR_INVALID, "bank index %d out of range", idx);
+    SpatialW* w = h->readers[idx];
+    if (C != w->C) fail(HV_ERR_INVALID, "bank %d has width %lld, block '%s' has %d", idx, (long long)C, w->name.c_str(), w->C);
+    const int64_t n = B_ref * L * C;
+    if (w->bank == nullptr || w->bank_B * w->bank_L != B_ref * L) w->bank = h->dmalloc(n);
+    w->bank_B = B_ref;
+    w->bank_L = L;
+    ck(cudaMemcpyAsync(w->bank, dev_ptr, static_cast<size_t>(n) * 2, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "bank copy");
+  });
+}
+
+int hv_clear_ref_banks(hv_handle h) {
+  if (!h) return HV_ERR_INVALID;
+  for (SpatialW* w : h->readers) {
+    w->bank = nullptr;  // storage stays in `owned` and is released with the handle
+    w->bank_B = w->bank_L = 0;
+  }
+  return HV_OK;
+}
+
+static size_t measure(hv_model* h, int B, int F, int H, int W) {
+  h->begin(nullptr, 0, true, nullptr);
+  if (h->cfg.kind == HV_KIND_UNET3D) {
+    static __half dummy;
+    h->unet_forward(&dummy, 0, &dummy, &dummy, &dummy, B, F, H, W, HV_FLAG_CFG);
+  } else if (h->cfg.kind == HV_KIND_POSE_GUIDER) {
+    h->pose_guider_forward(nullptr, nullptr, B, F, H, W);
+  } else {
+    h->camera_forward(nullptr, nullptr, B, F, H, W);
+  }
+  return h->ar.peak + 4096;
+}
+
+size_t hv_workspace_bytes(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width) {
+  if (!h || !h->finalized) return 0;
+  try {
+    return measure(h, B, F, height, width);
+  } catch (const Err& e) {
+    h->err = e.msg;
+    return 0;
+  }
+}
+
+int hv_unet3d_forward(hv_handle h, const void* sample, int64_t timestep, const void* ehs, const void* pose, void* out, int32_t B, int32_t F,
+                      int32_t height, int32_t width, uint32_t flags, void* workspace, size_t ws_bytes, hv_stream_t stream) {
+  if (!h || !sample || !ehs || !out) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized || h->cfg.kind != HV_KIND_UNET3D) fail(HV_ERR_STATE, "handle is not a finalized UNet3D");
+    const size_t need = measure(h, B, F, height, width);
+    size_t have = 0;
+    void* ws = get_ws(h, workspace, ws_bytes, need, &have);
+    h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
+    h->unet_forward(static_cast<const __half*>(sample), timestep, static_cast<const __half*>(ehs), static_cast<const __half*>(pose),
+                    static_cast<__half*>(out), B, F, height, width, flags);
+  });
+}
+
+int hv_pose_guider_forward(hv_handle h, const void* cond, void* out, int32_t B, int32_t F, int32_t H, int32_t W, void* workspace,
+                           size_t ws_bytes, hv_stream_t stream) {
+  if (!h || !cond || !out) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized || h->cfg.kind != HV_KIND_POSE_GUIDER) fail(HV_ERR_STATE, "handle is not a finalized PoseGuider");
+    const size_t need = measure(h, B, F, H, W);
+    size_t have = 0;
+    void* ws = get_ws(h, workspace, ws_bytes, need, &have);
+    h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
+    h->pose_guider_forward(static_cast<const __half*>(cond), static_cast<__half*>(out), B, F, H, W);
+  });
+}
+
+int hv_camera_encoder_forward(hv_handle h, const void* plucker, void* out, int32_t B, int32_t F, int32_t H, int32_t W, void* workspace,
+                              size_t ws_bytes, hv_stream_t stream) {
+  if (!h || !plucker || !out) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized || h->cfg.kind != HV_KIND_CAMERA_ENCODER) fail(HV_ERR_STATE, "handle is not a finalized CameraPoseEncoder");
+    const size_t need = measure(h, B, F, H, W);
+    size_t have = 0;
+    void* ws = get_ws(h, workspace, ws_bytes, need, &have);
+    h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
+    h->camera_forward(static_cast<const __half*>(plucker), static_cast<__half*>(out), B, F, H, W);
+  });
+}
+
+}  // extern "C"

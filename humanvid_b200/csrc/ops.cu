@@ -1,0 +1,179 @@
+#include "ops.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "gemm.cuh"
+#include "kernels.h"
+#include "tma.h"
+
+namespace hv {
+
+namespace {
+thread_local char g_msg[512] = "";
+int g_sms = 0;
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_msg, sizeof g_msg, fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return HV_ERR_CUDA;
+}
+
+int device_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    if (prop.major != 10) {
+      set_error("libhv_b200 needs an sm_100 device (found sm_%d%d)", prop.major, prop.minor);
+      return 0;
+    }
+    g_sms = prop.multiProcessorCount;
+  }
+  return g_sms;
+}
+
+static void fill_epilogue(GemmEpilogue& e, const hv_epilogue* ep, __half* out, int64_t ldc, int64_t N) {
+  e.out = out;
+  e.ldc = static_cast<int>(ldc);
+  e.n_valid = static_cast<int>(N);
+  if (ep) {
+    e.bias = static_cast<const __half*>(ep->bias);
+    e.rowvec = static_cast<const __half*>(ep->rowvec);
+    e.rowvec_ld = ep->rowvec_ld;
+    e.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    e.residual = static_cast<const __half*>(ep->residual);
+    e.ldr = ep->ldr;
+    e.act = ep->act;
+    e.geglu = ep->geglu;
+    if (ep->geglu) e.n_valid = static_cast<int>(N / 2);
+    if (ep->n_valid > 0) e.n_valid = ep->n_valid;
+  }
+}
+
+static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
+  if (geglu) return 256;
+  if (N <= 128) return 128;
+  // prefer 256-wide tiles (half the A re-reads, full-rate UMMA) unless that leaves most SMs idle
+  const int64_t t256 = m_tiles * ((N + 255) / 256);
+  if (N % 256 != 0 && N % 256 <= 128 && t256 < 2 * sms) return 128;
+  return t256 >= sms / 2 ? 256 : 128;
+}
+
+int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_t K1, const __half* W, __half* out, int64_t ldc,
+            int64_t M, int64_t N, int64_t K, const hv_epilogue* ep, cudaStream_t stream) {
+  const int sms = device_sms();
+  if (!sms) return HV_ERR_CUDA;
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) || (lda % 8) || (ldc % 8) || (N % 8)) {
+    set_error("hv_op_gemm: bad shape M=%lld N=%lld K=%lld lda=%lld ldc=%lld", (long long)M, (long long)N, (long long)K, (long long)lda,
+              (long long)ldc);
+    return HV_ERR_INVALID;
+  }
+  const bool split = A2 != nullptr && K1 > 0;
+  if (split && ((K1 % 64) || (lda2 % 8) || K1 >= K)) {
+    set_error("hv_op_gemm: split K1=%lld must be a multiple of 64 and < K", (long long)K1);
+    return HV_ERR_INVALID;
+  }
+  const bool geglu = ep && ep->geglu;
+  if (geglu && (N % 256)) {
+    set_error("hv_op_gemm: geglu needs N %% 256 == 0 (N=%lld)", (long long)N);
+    return HV_ERR_INVALID;
+  }
+  CUtensorMap ma0, ma1, mb;
+  const int64_t Ka = split ? K1 : K;
+  if (!make_map_2d(&ma0, A, M, Ka, lda, 128)) { set_error("hv_op_gemm A map: %s", tma_last_error()); return HV_ERR_TMA; }
+  ma1 = ma0;
+  if (split && !make_map_2d(&ma1, A2, M, K - K1, lda2, 128)) { set_error("hv_op_gemm A2 map: %s", tma_last_error()); return HV_ERR_TMA; }
+  const int64_t m_tiles = (M + 127) / 128;
+  const int bn = pick_block_n(N, m_tiles, geglu, sms);
+  if (!make_map_2d(&mb, W, N, K, K, bn)) { set_error("hv_op_gemm W map: %s", tma_last_error()); return HV_ERR_TMA; }
+  GemmProblem p;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.num_k_blocks = static_cast<int>((K + 63) / 64);
+  p.a_mode = A_LINEAR;
+  p.k_split = split ? static_cast<int>(K1 / 64) : 0;
+  GemmEpilogue e;
+  fill_epilogue(e, ep, out, ldc, N);
+  cudaError_t err = launch_gemm(ma0, ma1, mb, p, e, bn, sms, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "hv_op_gemm launch");
+  return HV_OK;
+}
+
+int op_gemm_batched_b(const __half* A, int64_t lda, const __half* X, int64_t ldx, __half* out, int64_t ldc, int64_t M, int64_t batch,
+                      int64_t rows, int64_t out_stride, int64_t K, cudaStream_t stream) {
+  const int sms = device_sms();
+  if (!sms) return HV_ERR_CUDA;
+  if (M <= 0 || batch <= 0 || rows <= 0 || (K % 8) || (lda % 8) || (ldx % 8) || (ldc % 8) || (out_stride % 8) || out_stride < rows) {
+    set_error("hv_op_gemm_batched_b: bad shape M=%lld batch=%lld rows=%lld stride=%lld K=%lld", (long long)M, (long long)batch, (long long)rows,
+              (long long)out_stride, (long long)K);
+    return HV_ERR_INVALID;
+  }
+  CUtensorMap ma, mb;
+  if (!make_map_2d(&ma, A, M, K, lda, 128)) { set_error("gemm_batched_b A map: %s", tma_last_error()); return HV_ERR_TMA; }
+  const int64_t m_tiles = (M + 127) / 128;
+  const int bn = (rows > 128 && m_tiles * batch * ((rows + 255) / 256) >= sms / 2) ? 256 : 128;
+  if (!make_map_3d(&mb, X, batch, rows, K, ldx, bn)) { set_error("gemm_batched_b X map: %s", tma_last_error()); return HV_ERR_TMA; }
+  GemmProblem p;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(rows);
+  p.num_k_blocks = static_cast<int>((K + 63) / 64);
+  p.a_mode = A_LINEAR;
+  p.b_batch = static_cast<int>(batch);
+  p.b_rows = static_cast<int>(rows);
+  p.b_out_stride = static_cast<int>(out_stride);
+  GemmEpilogue e;
+  e.out = out;
+  e.ldc = static_cast<int>(ldc);
+  e.n_valid = static_cast<int>(rows);
+  cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "hv_op_gemm_batched_b launch");
+  return HV_OK;
+}
+
+int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin,
+               int64_t Cout, int stride, const hv_epilogue* ep, cudaStream_t stream) {
+  const int sms = device_sms();
+  if (!sms) return HV_ERR_CUDA;
+  if ((Cin % 64) || (Cout % 8) || (ldc % 8) || (stride != 1 && stride != 2) || NF <= 0 || H <= 0 || W <= 0) {
+    set_error("hv_op_conv3x3: bad shape NF=%lld H=%lld W=%lld Cin=%lld Cout=%lld stride=%d", (long long)NF, (long long)H, (long long)W,
+              (long long)Cin, (long long)Cout, stride);
+    return HV_ERR_INVALID;
+  }
+  const int64_t Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+  GemmProblem p;
+  p.a_mode = stride == 1 ? A_CONV3X3 : A_CONV3X3_S2;
+  p.N = static_cast<int>(Cout);
+  p.cin_blocks = static_cast<int>(Cin / 64);
+  p.cin = static_cast<int>(Cin);
+  p.num_k_blocks = 9 * p.cin_blocks;
+  p.H = static_cast<int>(Ho);
+  p.W = static_cast<int>(Wo);
+  p.NF = static_cast<int>(NF);
+  choose_conv_box(p.NF, p.H, p.W, &p.bn, &p.bh, &p.bw);
+  p.tiles_n = (p.NF + p.bn - 1) / p.bn;
+  p.tiles_y = (p.H + p.bh - 1) / p.bh;
+  p.tiles_x = (p.W + p.bw - 1) / p.bw;
+  p.M = p.NF * p.H * p.W;
+  CUtensorMap ma, mb;
+  bool ok = stride == 1 ? make_map_nhwc(&ma, X, NF, H, W, Cin, p.bn, p.bh, p.bw) : make_map_nhwc_s2(&ma, X, NF, H, W, Cin, p.bn, p.bh, p.bw);
+  if (!ok) { set_error("hv_op_conv3x3 X map: %s", tma_last_error()); return HV_ERR_TMA; }
+  const int64_t m_tiles = static_cast<int64_t>(p.tiles_n) * p.tiles_y * p.tiles_x;
+  const int bn = pick_block_n(Cout, m_tiles, false, sms);
+  if (!make_map_2d(&mb, Wp, Cout, 9 * Cin, 9 * Cin, bn)) { set_error("hv_op_conv3x3 W map: %s", tma_last_error()); return HV_ERR_TMA; }
+  GemmEpilogue e;
+  fill_epilogue(e, ep, out, ldc, Cout);
+  cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream);
+  if (err != cudaSuccess) return cuda_fail(err, "hv_op_conv3x3 launch");
+  return HV_OK;
+}
+
+}  // namespace hv

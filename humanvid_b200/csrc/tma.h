@@ -1,0 +1,30 @@
+// Host-side construction of TMA tensor maps (cuTensorMapEncodeTiled resolved at run time through the CUDA
+// runtime's driver-entry-point API, so the library has no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hv {
+
+// fp16 row-major matrix [rows][ld] of which `cols` columns are valid; box = box_rows x 64 columns, 128B swizzle.
+// Out-of-bounds box elements read as zero.
+bool make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+// Same with an explicit box width (<= 64 columns).
+bool make_map_2d_box(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+
+// channels-last activation (N, H, W, C) fp16 -> 4-D map (C, W, H, N), box (64, bw, bh, bn).
+bool make_map_nhwc(CUtensorMap* m, const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C, int bn, int bh, int bw);
+
+// channels-last activation viewed as (N, H/2, 2, W/2, 2C) -> 5-D map, box (64, bw, 1, bh, bn): the operand view of a
+// stride-2 3x3 convolution (H and W must be even).
+bool make_map_nhwc_s2(CUtensorMap* m, const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C, int bn, int bh, int bw);
+
+// fp16 [batch][rows][ld] (cols valid) -> 3-D map (cols, rows, batch), box (64, box_rows, 1); rows beyond `rows` read as zero
+// even when the next batch item follows in memory.
+bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+const char* tma_last_error();
+
+}  // namespace hv

@@ -1,0 +1,662 @@
+"""Reference-facing modules of the B200-native denoising path.
+
+``UNet3DConditionModel``, ``PoseGuider`` and ``CameraPoseEncoder`` keep the reference's constructor arguments,
+``forward`` signatures, attribute names and ``state_dict`` keys, so
+``scripts/pose2vid.py``-style drivers build, load and call them unchanged:
+
+  * ``UNet3DConditionModel.forward``  <->  src/models/unet_3d.py:397-577
+  * ``PoseGuider.forward``            <->  src/models/pose_guider.py:51-61
+  * ``CameraPoseEncoder.forward``     <->  src/cameractrl/pose_adaptor.py:232-248
+
+The ``nn.Module`` tree below only *holds parameters* under the reference's names (torch is plumbing: device memory,
+``load_state_dict``, ``.to()``); none of its sub-modules' ``forward`` is ever executed.  All arithmetic happens in
+``libhv_b200.so`` (hand-written sm_100a CUDA) through the C ABI in ``include/hv_b200.h``.  There is no PyTorch or
+CPU fallback: without the library, or on a non-CUDA tensor, ``forward`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+
+# --------------------------------------------------------------------------------------------- parameter shells
+class _Shell(nn.Module):
+    """Parameter container; never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("humanvid_b200 parameter shells are not executable; call the owning network's forward")
+
+
+def _conv(cin, cout, k, **kw):
+    return nn.Conv2d(cin, cout, k, **kw)
+
+
+class _Attention(_Shell):
+    """diffusers Attention parameter names: to_q/to_k/to_v (no bias), to_out.0 (bias)."""
+
+    def __init__(self, dim, cross_dim=None):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(cross_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(cross_dim or dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+
+
+class _GEGLU(_Shell):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = nn.Linear(dim, dim * 8)
+
+
+class _FeedForward(_Shell):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class TemporalBasicTransformerBlock(_Shell):
+    """Parameter shell of src/models/attention.py:298-379; ``bank`` is what ReferenceAttentionControl.update fills."""
+
+    def __init__(self, dim, cross_attention_dim):
+        super().__init__()
+        self.attn1 = _Attention(dim)
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn2 = _Attention(dim, cross_attention_dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ff = _FeedForward(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.bank: List[torch.Tensor] = []
+
+
+class _Transformer3D(_Shell):
+    def __init__(self, ch, cross_attention_dim, groups):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.proj_in = _conv(ch, ch, 1)
+        self.transformer_blocks = nn.ModuleList([TemporalBasicTransformerBlock(ch, cross_attention_dim)])
+        self.proj_out = _conv(ch, ch, 1)
+
+
+def _sinusoid(max_len, dim):
+    pos = torch.arange(max_len).unsqueeze(1)
+    div = torch.exp(torch.arange(0, dim, 2) * (-math.log(10000.0) / dim))
+    pe = torch.zeros(1, max_len, dim)
+    pe[0, :, 0::2] = torch.sin(pos * div)
+    pe[0, :, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class _PosEnc(_Shell):
+    def __init__(self, dim, max_len):
+        super().__init__()
+        self.register_buffer("pe", _sinusoid(max_len, dim))
+
+
+class _TemporalAttention(_Attention):
+    def __init__(self, dim, max_len):
+        super().__init__(dim)
+        self.pos_encoder = _PosEnc(dim, max_len)
+
+
+class _TemporalBlock(_Shell):
+    def __init__(self, dim, n_attn, max_len):
+        super().__init__()
+        self.attention_blocks = nn.ModuleList([_TemporalAttention(dim, max_len) for _ in range(n_attn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in range(n_attn)])
+        self.ff = _FeedForward(dim)
+        self.ff_norm = nn.LayerNorm(dim)
+
+
+class _TemporalTransformer3D(_Shell):
+    def __init__(self, ch, max_len, groups):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.proj_in = nn.Linear(ch, ch)
+        self.transformer_blocks = nn.ModuleList([_TemporalBlock(ch, 2, max_len)])
+        self.proj_out = nn.Linear(ch, ch)
+
+
+class _MotionModule(_Shell):
+    def __init__(self, ch, max_len, groups):
+        super().__init__()
+        self.temporal_transformer = _TemporalTransformer3D(ch, max_len, groups)
+
+
+class _Resnet(_Shell):
+    def __init__(self, cin, cout, temb, groups):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-5)
+        self.conv1 = _conv(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-5)
+        self.conv2 = _conv(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.conv_shortcut = _conv(cin, cout, 1)
+
+
+class _Sampler(_Shell):
+    def __init__(self, ch, stride):
+        super().__init__()
+        self.conv = _conv(ch, ch, 3, stride=stride, padding=1)
+
+
+class _Block(_Shell):
+    def __init__(self, res_io, ch, attn, motion, xdim, temb, groups, max_len, sampler=None):
+        super().__init__()
+        if attn:
+            self.attentions = nn.ModuleList([_Transformer3D(ch, xdim, groups) for _ in range(attn)])
+        self.resnets = nn.ModuleList([_Resnet(i, o, temb, groups) for i, o in res_io])
+        self.motion_modules = nn.ModuleList([_MotionModule(ch, max_len, groups) if motion else None for _ in range(max(attn, len(res_io)) if sampler != "mid" else 1)])
+        if sampler == "down":
+            self.downsamplers = nn.ModuleList([_Sampler(ch, 2)])
+        elif sampler == "up":
+            self.upsamplers = nn.ModuleList([_Sampler(ch, 1)])
+
+
+class _TimestepEmbedding(_Shell):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+
+@dataclass
+class UNet3DConditionOutput:
+    sample: torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------- native base
+class _NativeNet(nn.Module):
+    """Owns one ``hv_handle``; pushes the module's state_dict into it whenever parameters changed."""
+
+    _kind = 0
+
+    def __init__(self):
+        super().__init__()
+        self._handle = None
+        self._pushed_versions = None
+        self._epoch = 0
+
+    def _hv_config(self) -> "HvConfig":  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _versions(self):
+        # cheap fingerprint checked on every forward; full re-push is forced by load_state_dict()/.to()/.half()
+        p = next(self.parameters())
+        return (p.data_ptr(), p._version, p.dtype, self._epoch)
+
+    def _apply(self, fn, *a, **k):
+        self._epoch = getattr(self, "_epoch", 0) + 1
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._epoch = getattr(self, "_epoch", 0) + 1
+        return super().load_state_dict(*a, **k)
+
+    def refresh_native(self):
+        """Call after modifying parameters in place: the packed device copy is rebuilt on the next forward."""
+        self._epoch = getattr(self, "_epoch", 0) + 1
+
+    def _destroy(self):
+        if self._handle is not None:
+            N.lib().hv_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def _sync_native(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("humanvid_b200 runs on CUDA (B200) only: move the module with .to('cuda', torch.float16); there is no CPU path")
+        ver = self._versions()
+        if self._handle is not None and ver == self._pushed_versions:
+            return self._handle
+        self._destroy()
+        lib = N.lib()
+        cfg = self._hv_config()
+        h = C.c_void_p()
+        N.check(lib.hv_create(C.byref(cfg), C.byref(h)))
+        st = N.stream()
+        for k, v in self.state_dict().items():
+            if v.dtype == torch.float16:
+                dt = 0
+            elif v.dtype == torch.float32:
+                dt = 1
+            else:
+                raise RuntimeError(f"parameter {k} has dtype {v.dtype}; humanvid_b200 ingests fp16 or fp32 weights")
+            t = v.detach().contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*(t.shape if t.dim() else (1,)))
+            N.check(lib.hv_set_weight(h, k.encode(), N.ptr(t), shape, N.i32(max(t.dim(), 1)), N.i32(dt), st), h)
+        N.check(lib.hv_finalize(h, st), h)
+        torch.cuda.current_stream().synchronize()
+        self._handle = h
+        self._pushed_versions = ver
+        return h
+
+    @staticmethod
+    def _as_half(x: torch.Tensor, what: str) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(f"{what} must be a CUDA tensor (humanvid_b200 has no CPU path)")
+        return x.to(torch.float16).contiguous()
+
+    @property
+    def last_launch_count(self) -> int:
+        if self._handle is None:
+            return 0
+        f = N.lib().hv_last_launch_count
+        f.restype = C.c_int64
+        return int(f(self._handle))
+
+
+class HvConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("in_channels", C.c_int32),
+        ("out_channels", C.c_int32),
+        ("block_out_channels", C.c_int32 * 4),
+        ("heads", C.c_int32),
+        ("cross_attention_dim", C.c_int32),
+        ("norm_groups", C.c_int32),
+        ("use_motion_module", C.c_int32),
+        ("motion_max_len", C.c_int32),
+        ("pg_cond_channels", C.c_int32),
+        ("pg_block_channels", C.c_int32 * 4),
+        ("pg_out_channels", C.c_int32),
+        ("cam_downscale", C.c_int32),
+        ("cam_cin", C.c_int32),
+        ("cam_channels", C.c_int32),
+        ("cam_nums_rb", C.c_int32),
+        ("cam_heads", C.c_int32),
+        ("cam_max_len", C.c_int32),
+    ]
+
+
+# --------------------------------------------------------------------------------------------- UNet3DConditionModel
+class UNet3DConditionModel(_NativeNet):
+    """Drop-in for src/models/unet_3d.py:30-577 (inference): same ctor keywords, forward signature, state_dict keys."""
+
+    _kind = 0
+
+    def __init__(
+        self,
+        sample_size: Optional[int] = None,
+        in_channels: int = 4,
+        out_channels: int = 4,
+        center_input_sample: bool = False,
+        flip_sin_to_cos: bool = True,
+        freq_shift: int = 0,
+        down_block_types: Tuple[str, ...] = ("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+        mid_block_type: str = "UNetMidBlock3DCrossAttn",
+        up_block_types: Tuple[str, ...] = ("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+        only_cross_attention=False,
+        block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280),
+        layers_per_block: int = 2,
+        downsample_padding: int = 1,
+        mid_block_scale_factor: float = 1,
+        act_fn: str = "silu",
+        norm_num_groups: int = 32,
+        norm_eps: float = 1e-5,
+        cross_attention_dim: int = 1280,
+        attention_head_dim=8,
+        dual_cross_attention: bool = False,
+        use_linear_projection: bool = False,
+        class_embed_type=None,
+        num_class_embeds=None,
+        upcast_attention: bool = False,
+        resnet_time_scale_shift: str = "default",
+        use_inflated_groupnorm=False,
+        use_motion_module=False,
+        motion_module_resolutions=(1, 2, 4, 8),
+        motion_module_mid_block=False,
+        motion_module_decoder_only=False,
+        motion_module_type=None,
+        motion_module_kwargs=None,
+        unet_use_cross_frame_attention=None,
+        unet_use_temporal_attention=None,
+    ):
+        super().__init__()
+        mmk = dict(motion_module_kwargs or {})
+        unsupported = []
+        if tuple(down_block_types) != ("CrossAttnDownBlock3D",) * 3 + ("DownBlock3D",) or tuple(up_block_types) != ("UpBlock3D",) + ("CrossAttnUpBlock3D",) * 3:
+            unsupported.append("block types other than the SD1.5 layout")
+        if layers_per_block != 2 or len(block_out_channels) != 4:
+            unsupported.append("layers_per_block != 2 / depth != 4")
+        if center_input_sample or not flip_sin_to_cos or freq_shift != 0 or use_linear_projection or dual_cross_attention:
+            unsupported.append("center_input_sample / flip_sin_to_cos=False / freq_shift / use_linear_projection / dual_cross_attention")
+        if class_embed_type is not None or num_class_embeds is not None or unet_use_temporal_attention or unet_use_cross_frame_attention:
+            unsupported.append("class embeddings / unet_use_temporal_attention / cross_frame_attention")
+        if resnet_time_scale_shift != "default" or act_fn not in ("silu", "swish") or mid_block_scale_factor != 1 or not isinstance(attention_head_dim, int):
+            unsupported.append("non-default resnet/act options")
+        if use_motion_module and (
+            tuple(motion_module_resolutions) != (1, 2, 4, 8) or not motion_module_mid_block or motion_module_decoder_only
+            or motion_module_type != "Vanilla" or mmk.get("num_transformer_block", 1) != 1
+            or tuple(mmk.get("attention_block_types", ("Temporal_Self", "Temporal_Self"))) != ("Temporal_Self", "Temporal_Self")
+            or not mmk.get("temporal_position_encoding", False) or mmk.get("temporal_attention_dim_div", 1) != 1
+        ):
+            unsupported.append("motion-module layout other than configs/inference/inference_v2.yaml")
+        if unsupported:
+            raise NotImplementedError("humanvid_b200.UNet3DConditionModel implements the inference_v2 hot path only; unsupported: " + "; ".join(unsupported))
+        self.config = SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("self", "mmk", "unsupported", "__class__")})
+        self.sample_size = sample_size
+        self.in_channels = in_channels
+        ch = list(block_out_channels)
+        heads, xdim, g = attention_head_dim, cross_attention_dim, norm_num_groups
+        temb = ch[0] * 4
+        mm = bool(use_motion_module)
+        max_len = mmk.get("temporal_position_encoding_max_len", 24)
+        self._heads, self._max_len, self._mm = heads, max_len, mm
+        self.conv_in = _conv(in_channels, ch[0], 3, padding=1)
+        self.time_embedding = _TimestepEmbedding(ch[0], temb)
+        self.down_blocks = nn.ModuleList([])
+        self.mid_block = None
+        self.up_blocks = nn.ModuleList([])
+        prev = ch[0]
+        for i, c in enumerate(ch):
+            last = i == 3
+            self.down_blocks.append(_Block([(prev, c), (c, c)], c, 0 if last else 2, mm, xdim, temb, g, max_len, None if last else "down"))
+            prev = c
+        self.mid_block = _Block([(ch[3], ch[3]), (ch[3], ch[3])], ch[3], 1, mm, xdim, temb, g, max_len, "mid")
+        rev = ch[::-1]
+        prev = rev[0]
+        for i, c in enumerate(rev):
+            cin = rev[min(i + 1, 3)]
+            io = [((prev if j == 0 else c) + (cin if j == 2 else c), c) for j in range(3)]
+            self.up_blocks.append(_Block(io, c, 0 if i == 0 else 3, mm, xdim, temb, g, max_len, "up" if i < 3 else None))
+            prev = c
+        self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=norm_eps)
+        self.conv_out = _conv(ch[0], out_channels, 3, padding=1)
+        self._ref_cfg = True
+
+    # ---- reference banks (ReferenceAttentionControl, read side) -----------------------------------------------
+    def reader_blocks(self) -> List[TemporalBasicTransformerBlock]:
+        """fusion_blocks='full' order of mutual_self_attention.py:284-300."""
+
+        def dfs(m):
+            out = [m]
+            for c in m.children():
+                out += dfs(c)
+            return out
+
+        mods = [m for m in dfs(self) if isinstance(m, TemporalBasicTransformerBlock)]
+        return sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
+
+    def _push_banks(self, h):
+        lib = N.lib()
+        blocks = self.reader_blocks()
+        any_bank = any(len(b.bank) > 0 for b in blocks)
+        N.check(lib.hv_clear_ref_banks(h), h)
+        if not any_bank:
+            return
+        st = N.stream()
+        for i, b in enumerate(blocks):
+            if len(b.bank) == 0:
+                continue
+            if len(b.bank) != 1:
+                raise NotImplementedError("one reference bank per block is supported (the pipeline writes exactly one)")
+            t = self._as_half(b.bank[0], "reference bank")
+            N.check(lib.hv_set_ref_bank(h, N.i32(i), N.ptr(t), N.i64(t.shape[0]), N.i64(t.shape[1]), N.i64(t.shape[2]), st), h)
+
+    def _hv_config(self):
+        c = self.config
+        cfg = HvConfig()
+        cfg.kind = 0
+        cfg.in_channels, cfg.out_channels = c.in_channels, c.out_channels
+        cfg.block_out_channels = (C.c_int32 * 4)(*c.block_out_channels)
+        cfg.heads, cfg.cross_attention_dim, cfg.norm_groups = c.attention_head_dim, c.cross_attention_dim, c.norm_num_groups
+        cfg.use_motion_module, cfg.motion_max_len = int(self._mm), self._max_len
+        return cfg
+
+    def workspace_bytes(self, B, F, h, w) -> int:
+        hd = self._sync_native()
+        f = N.lib().hv_workspace_bytes
+        f.restype = C.c_size_t
+        return int(f(hd, N.i32(B), N.i32(F), N.i32(h), N.i32(w)))
+
+    @torch.no_grad()
+    def forward(
+        self,
+        sample: torch.Tensor,
+        timestep: Union[torch.Tensor, float, int],
+        encoder_hidden_states: torch.Tensor,
+        class_labels: Optional[torch.Tensor] = None,
+        pose_cond_fea: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
+        mid_block_additional_residual: Optional[torch.Tensor] = None,
+        return_dict: bool = True,
+    ):
+        if class_labels is not None or attention_mask is not None or down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+            raise NotImplementedError("class_labels / attention_mask / additional residuals are not part of the CamAnimate inference path")
+        if sample.dim() != 5:
+            raise ValueError(f"Expected sample to have ndim=5 (b c f h w), got {sample.dim()}")
+        B, Cc, F, H, W = sample.shape
+        if Cc != self.in_channels:
+            raise ValueError(f"sample has {Cc} channels, model expects {self.in_channels}")
+        h = self._sync_native()
+        self._push_banks(h)
+        x = self._as_half(sample, "sample")
+        ehs = self._as_half(encoder_hidden_states, "encoder_hidden_states")
+        if ehs.shape[0] != B or ehs.shape[1] != 1:
+            raise ValueError(f"encoder_hidden_states must be (batch, 1, dim) with batch {B}; got {tuple(ehs.shape)}")
+        pose = None if pose_cond_fea is None else self._as_half(pose_cond_fea, "pose_cond_fea")
+        if pose is not None and tuple(pose.shape) != (B, self.config.block_out_channels[0], F, H, W):
+            raise ValueError(f"pose_cond_fea must be {(B, self.config.block_out_channels[0], F, H, W)}, got {tuple(pose.shape)}")
+        t = int(timestep.reshape(-1)[0].item()) if torch.is_tensor(timestep) else int(timestep)
+        out = torch.empty((B, self.config.out_channels, F, H, W), device=x.device, dtype=torch.float16)
+        flags = 1 if self._ref_cfg else 0
+        N.check(N.lib().hv_unet3d_forward(h, N.ptr(x), N.i64(t), N.ptr(ehs), N.ptr(pose), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W),
+                                          C.c_uint32(flags), None, C.c_size_t(0), N.stream()), h)
+        out = out.to(sample.dtype) if sample.dtype != torch.float16 else out
+        if not return_dict:
+            return (out,)
+        return UNet3DConditionOutput(sample=out)
+
+    # ---- loading (unet_3d.py:579-670) ---------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, motion_module_path, subfolder=None, unet_additional_kwargs=None, mm_zero_proj_out=False):
+        path = os.path.join(str(pretrained_model_path), subfolder) if subfolder is not None else str(pretrained_model_path)
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = json.load(f)
+        cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
+        cfg["down_block_types"] = ["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"]
+        cfg["up_block_types"] = ["UpBlock3D"] + ["CrossAttnUpBlock3D"] * 3
+        cfg["mid_block_type"] = "UNetMidBlock3DCrossAttn"
+        import inspect
+
+        allowed = set(inspect.signature(cls.__init__).parameters)
+        kw = {k: v for k, v in cfg.items() if k in allowed}
+        kw.update(unet_additional_kwargs or {})
+        model = cls(**kw)
+        st_path = os.path.join(path, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.torch import load_file
+
+            state = load_file(st_path, device="cpu")
+        else:
+            state = torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu", weights_only=True)
+        mp = str(motion_module_path)
+        if os.path.isfile(mp):
+            if mp.endswith(".safetensors"):
+                from safetensors.torch import load_file
+
+                mm_state = load_file(mp, device="cpu")
+            else:
+                mm_state = torch.load(mp, map_location="cpu", weights_only=True)
+            if mm_zero_proj_out:
+                mm_state = {k: v for k, v in mm_state.items() if "proj_out" not in k}
+            state.update({k: v for k, v in mm_state.items() if "motion_modules" in k})
+        model.load_state_dict(state, strict=False)
+        return model
+
+
+# --------------------------------------------------------------------------------------------- PoseGuider
+class PoseGuider(_NativeNet):
+    """Drop-in for src/models/pose_guider.py:16-61."""
+
+    def __init__(self, conditioning_embedding_channels: int, conditioning_channels: int = 3, block_out_channels: Tuple[int, ...] = (16, 32, 64, 128)):
+        super().__init__()
+        if len(block_out_channels) != 4:
+            raise NotImplementedError("PoseGuider with 4 resolution levels only")
+        ch = list(block_out_channels)
+        self._cfg = (conditioning_embedding_channels, conditioning_channels, ch)
+        self.conv_in = _conv(conditioning_channels, ch[0], 3, padding=1)
+        self.blocks = nn.ModuleList([])
+        for a, b in zip(ch[:-1], ch[1:]):
+            self.blocks.append(_conv(a, a, 3, padding=1))
+            self.blocks.append(_conv(a, b, 3, padding=1, stride=2))
+        self.conv_out = _conv(ch[-1], conditioning_embedding_channels, 3, padding=1)
+        nn.init.zeros_(self.conv_out.weight)  # zero_module (pose_guider.py:42)
+        nn.init.zeros_(self.conv_out.bias)
+
+    def _hv_config(self):
+        out, cin, ch = self._cfg
+        cfg = HvConfig()
+        cfg.kind = 1
+        cfg.pg_cond_channels, cfg.pg_out_channels = cin, out
+        cfg.pg_block_channels = (C.c_int32 * 4)(*ch)
+        cfg.norm_groups = 32
+        return cfg
+
+    @torch.no_grad()
+    def forward(self, conditioning: torch.Tensor) -> torch.Tensor:
+        if conditioning.dim() != 5:
+            raise ValueError("conditioning must be (b, c, f, h, w)")
+        B, Cc, F, H, W = conditioning.shape
+        h = self._sync_native()
+        x = self._as_half(conditioning, "conditioning")
+        out = torch.empty((B, self._cfg[0], F, H // 8, W // 8), device=x.device, dtype=torch.float16)
+        N.check(N.lib().hv_pose_guider_forward(h, N.ptr(x), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W), None, C.c_size_t(0), N.stream()), h)
+        return out.to(conditioning.dtype) if conditioning.dtype != torch.float16 else out
+
+
+# --------------------------------------------------------------------------------------------- CameraPoseEncoder
+class _CamResnet(_Shell):
+    def __init__(self, ch, ksize):
+        super().__init__()
+        self.block1 = _conv(ch, ch, 3, padding=1)
+        self.block2 = _conv(ch, ch, ksize, padding=ksize // 2)
+
+
+class CameraPoseEncoder(_NativeNet):
+    """Drop-in for src/cameractrl/pose_adaptor.py:160-248 with configs/inference/inference_v2.yaml pose_encoder_kwargs."""
+
+    def __init__(self, downscale_factor, channels=(320, 640, 1280, 1280), nums_rb=3, cin=64, ksize=3, sk=False, use_conv=True,
+                 compression_factor=1, temporal_attention_nhead=8, attention_block_types=("Temporal_Self",), temporal_position_encoding=False,
+                 temporal_position_encoding_max_len=16, rescale_output_factor=1.0):
+        super().__init__()
+        channels = list(channels)
+        if len(channels) != 1 or ksize != 1 or not sk or compression_factor != 1 or tuple(attention_block_types) != ("Temporal_Self",) \
+                or not temporal_position_encoding or rescale_output_factor != 1.0:
+            raise NotImplementedError("CameraPoseEncoder: only the inference_v2.yaml layout (one level, ksize=1, sk=True, Temporal_Self + PE) is implemented")
+        c = channels[0]
+        self._cfg = dict(downscale=downscale_factor, cin=cin, c=c, nums_rb=nums_rb, heads=temporal_attention_nhead, max_len=temporal_position_encoding_max_len)
+        self.channels = channels
+        self.nums_rb = nums_rb
+        self.encoder_down_conv_blocks = nn.ModuleList([nn.ModuleList([_CamResnet(c, ksize) for _ in range(nums_rb)])])
+        att = []
+        for _ in range(nums_rb):
+            blk = _Shell()
+            blk.attention_blocks = nn.ModuleList([_TemporalAttention(c, temporal_position_encoding_max_len)])
+            blk.norms = nn.ModuleList([nn.LayerNorm(c)])
+            blk.ff = _FeedForward(c)
+            blk.ff_norm = nn.LayerNorm(c)
+            att.append(blk)
+        self.encoder_down_attention_blocks = nn.ModuleList([nn.ModuleList(att)])
+        zc = _conv(c, c, 1, bias=False)
+        nn.init.zeros_(zc.weight)
+        self.zero_conv_layers = nn.ModuleList([zc])
+        self.encoder_conv_in = _conv(cin, c, 3, padding=1)
+
+    def _hv_config(self):
+        d = self._cfg
+        cfg = HvConfig()
+        cfg.kind = 2
+        cfg.cam_downscale, cfg.cam_cin, cfg.cam_channels = d["downscale"], d["cin"], d["c"]
+        cfg.cam_nums_rb, cfg.cam_heads, cfg.cam_max_len = d["nums_rb"], d["heads"], d["max_len"]
+        cfg.heads = d["heads"]
+        cfg.norm_groups = 32
+        return cfg
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        if x.dim() != 5:
+            raise ValueError("plucker embedding must be (b, c, f, h, w)")
+        B, Cc, F, H, W = x.shape
+        r = self._cfg["downscale"]
+        if Cc * r * r != self._cfg["cin"]:
+            raise ValueError(f"plucker embedding has {Cc} channels; encoder expects {self._cfg['cin'] // (r * r)}")
+        h = self._sync_native()
+        xin = self._as_half(x, "plucker embedding")
+        out = torch.empty((B * F, self._cfg["c"], H // r, W // r), device=xin.device, dtype=torch.float16)
+        N.check(N.lib().hv_camera_encoder_forward(h, N.ptr(xin), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W), None, C.c_size_t(0), N.stream()), h)
+        return [out.to(x.dtype) if x.dtype != torch.float16 else out]
+
+
+# --------------------------------------------------------------------------------------------- ReferenceAttentionControl (reader)
+class ReferenceAttentionControl:
+    """Reader side of src/models/mutual_self_attention.py for a native UNet3DConditionModel.
+
+    Same constructor keywords / ``update(writer)`` / ``clear()``.  ``writer`` is the reference's own
+    ReferenceAttentionControl(mode="write") around its PyTorch 2-D UNet (or anything exposing ``.unet`` whose
+    transformer blocks carry ``norm1`` and a ``bank`` list): banks are matched in the same sorted order.
+    The reference implements the read path by monkey-patching ``forward`` of every block and concatenating the bank;
+    here ``update`` hands the banks to the native attention kernel, which reads them as a second key/value segment.
+    """
+
+    def __init__(self, unet, mode="read", do_classifier_free_guidance=False, attention_auto_machine_weight=float("inf"),
+                 gn_auto_machine_weight=1.0, style_fidelity=1.0, reference_attn=True, reference_adain=False, fusion_blocks="midup",
+                 batch_size=1):
+        if mode != "read":
+            raise NotImplementedError("the native UNet is the reader; use the reference's ReferenceAttentionControl for mode='write'")
+        if fusion_blocks != "full" or reference_adain or not reference_attn:
+            raise NotImplementedError("only fusion_blocks='full', reference_attn=True (what pipeline_pose2vid_long.py uses)")
+        if not isinstance(unet, UNet3DConditionModel):
+            raise TypeError("unet must be a humanvid_b200.UNet3DConditionModel")
+        self.unet = unet
+        unet._ref_cfg = bool(do_classifier_free_guidance)
+        for m in unet.reader_blocks():
+            m.bank = []
+
+    @staticmethod
+    def _writer_blocks(writer):
+        root = writer.unet if hasattr(writer, "unet") else writer
+
+        def dfs(m):
+            out = [m]
+            for c in m.children():
+                out += dfs(c)
+            return out
+
+        mods = [m for m in dfs(root) if hasattr(m, "bank") and hasattr(m, "norm1") and hasattr(m, "attn1")]
+        return sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
+
+    def update(self, writer, dtype=torch.float16):
+        readers = self.unet.reader_blocks()
+        writers = self._writer_blocks(writer)
+        for r, w in zip(readers, writers):
+            r.bank = [v.clone().to(dtype) for v in w.bank]
+
+    def clear(self):
+        for r in self.unet.reader_blocks():
+            r.bank.clear()

@@ -1,0 +1,111 @@
+"""CPU tests of the drop-in boundary: the C-ABI library exports every symbol its headers declare, the Python shells
+expose the reference's state_dict keys / attributes, host-side glue (scheduler, windows) matches the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import hv_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    names = []
+    for h in ("hv_b200.h", "hv_b200_ops.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names += re.findall(r"\b(hv_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    from humanvid_b200 import _native
+
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_unet_shell_has_reference_state_dict_keys():
+    from humanvid_b200 import UNet3DConditionModel
+
+    kw = dict(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, use_motion_module=True, use_inflated_groupnorm=True,
+              motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True, motion_module_type="Vanilla",
+              motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                        temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1),
+              unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    m = UNet3DConditionModel(**kw)
+    o = O.UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64)
+    sm, so = m.state_dict(), o.state_dict()
+    assert set(sm) == set(so)
+    assert all(sm[k].shape == so[k].shape for k in so)
+    assert m.in_channels == 4 and m.config.block_out_channels == (32, 64, 128, 128)
+    # reader order == reference order (pin_report.json)
+    names = {id(b): n for n, b in m.named_modules()}
+    order = [names[id(b)] for b in m.reader_blocks()]
+    import json
+
+    rep = json.load(open(os.path.join(ROOT, "tests", "golden", "pin_report.json")))
+    assert order == rep["bank_order"]
+    # image variant (config 1): no motion modules
+    m1 = UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    o1 = O.UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, use_motion_module=False, use_inflated_groupnorm=False)
+    assert set(m1.state_dict()) == set(o1.state_dict())
+
+
+def test_pose_guider_and_camera_shells():
+    from humanvid_b200 import CameraPoseEncoder, PoseGuider
+
+    pg = PoseGuider(320, block_out_channels=(16, 32, 96, 256))
+    assert set(pg.state_dict()) == set(O.PoseGuider().state_dict())
+    assert float(pg.conv_out.weight.abs().sum()) == 0.0  # zero_module like the reference
+    cam = CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                            temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                            temporal_position_encoding_max_len=24)
+    so = O.CameraPoseEncoder().state_dict()
+    assert set(cam.state_dict()) == set(so)
+    assert all(cam.state_dict()[k].shape == so[k].shape for k in so)
+
+
+def test_forward_fails_loudly_without_cuda():
+    from humanvid_b200 import PoseGuider
+
+    pg = PoseGuider(320, block_out_channels=(16, 32, 96, 256))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pg(torch.zeros(1, 3, 1, 16, 16))
+
+
+def test_unsupported_configs_are_rejected():
+    from humanvid_b200 import UNet3DConditionModel
+
+    with pytest.raises(NotImplementedError):
+        UNet3DConditionModel(use_linear_projection=True)
+    with pytest.raises(NotImplementedError):
+        UNet3DConditionModel(layers_per_block=3)
+
+
+def test_scheduler_matches_oracle_ddim():
+    from humanvid_b200.scheduler import DDIMScheduler
+
+    s = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1, prediction_type="v_prediction",
+                      rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    s.set_timesteps(25)
+    o = O.DDIM()
+    ot = o.set_timesteps(25)
+    assert s.timesteps.tolist() == ot.tolist()
+    g = torch.Generator().manual_seed(0)
+    x, v = torch.randn(1, 4, 2, 8, 8, generator=g), torch.randn(1, 4, 2, 8, 8, generator=g)
+    for t in (999, 519, 39):
+        assert torch.allclose(s.step(v, t, x).prev_sample, o.step(v, t, x), atol=1e-6)
+
+
+def test_pipeline_windows_match_oracle():
+    from humanvid_b200.pipeline import uniform
+
+    for nf in (24, 48, 87):
+        assert [list(w) for w in uniform(0, 25, nf, 24, 1, 4)] == O.uniform_windows(0, nf, 24, 1, 4)

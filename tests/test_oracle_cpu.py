@@ -1,0 +1,128 @@
+"""CPU tests: the oracle against the golden vectors produced from the reference's own modules
+(oracle/pin_against_reference.py), plus the oracle-side known answers of SURVEY.md section 8c."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import hv_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def test_pin_report_is_exact():
+    rep = json.load(open(os.path.join(GOLD, "pin_report.json")))
+    for k in ("unet_narrow_motion", "unet_narrow_bank_cfg1", "unet_narrow_bank_cfg0", "unet_narrow_image", "unet_full_width", "pose_guider",
+              "camera_encoder", "plucker"):
+        assert rep[k] == 0.0, (k, rep[k])
+    assert rep["unet_full_params"] == 1312730244
+    # DFS(down, up, mid) stable-sorted by -width
+    assert rep["bank_order"][0].startswith("down_blocks.2") and rep["bank_order"][5].startswith("mid_block") and rep["bank_order"][-1].startswith("up_blocks.3")
+
+
+@pytest.fixture(scope="module")
+def narrow():
+    g = load("unet_narrow.pt")
+    m = O.UNet3DConditionModel(block_out_channels=tuple(g["chs"]), cross_attention_dim=g["xdim"]).eval()
+    O.synthetic_init(m, seed=g["seed"])
+    return m, g
+
+
+def test_unet_narrow_matches_reference_golden(narrow):
+    m, g = narrow
+    with torch.no_grad():
+        y = m(g["x"], torch.tensor(g["t"]), g["ehs"], pose_cond_fea=g["pose"])[0]
+    assert torch.allclose(y, g["y"], atol=1e-5, rtol=1e-5)
+
+
+def test_reference_bank_hook_golden_and_identities(narrow):
+    m, g = narrow
+    b = load("unet_narrow_bank.pt")
+    x, t, ehs, pose = g["x"], torch.tensor(g["t"]), g["ehs"], g["pose"]
+    O.set_reference_banks(m, b["banks"], cfg=True)
+    with torch.no_grad():
+        y = m(x, t, ehs, pose_cond_fea=pose)[0]
+    assert torch.allclose(y, b["y"], atol=1e-5, rtol=1e-5)
+    # CFG identity: the uncond half must equal the no-bank forward of the same rows
+    O.set_reference_banks(m, None)
+    with torch.no_grad():
+        y0 = m(x, t, ehs, pose_cond_fea=pose)[0]
+    assert torch.allclose(y[:1], y0[:1], atol=1e-5)
+    assert not torch.allclose(y[1:], y0[1:], atol=1e-3)
+
+
+def test_zero_init_branches_are_noops(narrow):
+    m, g = narrow
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        y0 = m(g["x"], torch.tensor(g["t"]), g["ehs"])[0]
+        for k, p in m.named_parameters():
+            if "motion_modules" in k and ".proj_out." in k and "transformer_blocks" not in k:
+                p.zero_()
+        y1 = m(g["x"], torch.tensor(g["t"]), g["ehs"])[0]
+        # with proj_out zeroed every motion module is an exact identity -> result equals a UNet without temporal mixing
+        xs = g["x"][:, :, :1].repeat(1, 1, 3, 1, 1)
+        y2 = m(xs, torch.tensor(g["t"]), g["ehs"])[0]
+    assert not torch.allclose(y0, y1)
+    assert torch.allclose(y2[:, :, 0], y2[:, :, 2], atol=1e-5)
+    m.load_state_dict(sd)
+
+
+def test_cross_attention_single_key_collapses():
+    torch.manual_seed(0)
+    a = O.Attention(64, cross_attention_dim=32, heads=8, dim_head=8)
+    x, e = torch.randn(3, 10, 64), torch.randn(3, 1, 32)
+    ref = a(x, encoder_hidden_states=e)
+    col = a.to_out[0](a.to_v(e))
+    assert torch.allclose(ref, col.expand_as(ref), atol=1e-6)
+
+
+def test_pose_guider_and_camera_encoder_golden():
+    g = load("pose_guider.pt")
+    m = O.synthetic_init(O.PoseGuider().eval(), seed=g["seed"])
+    with torch.no_grad():
+        assert torch.allclose(m(g["x"]), g["y"], atol=1e-5, rtol=1e-5)
+    g = load("camera_encoder.pt")
+    m = O.synthetic_init(O.CameraPoseEncoder().eval(), seed=g["seed"])
+    with torch.no_grad():
+        assert torch.allclose(m(g["x"])[0], g["y"], atol=1e-5, rtol=1e-5)
+
+
+def test_context_windows_and_counter_pattern():
+    w = O.uniform_windows(0, 48, 24, 1, 4)
+    assert [(a[0], a[-1]) for a in w] == [(0, 23), (20, 43), (40, 15)]
+    cnt = [0] * 48
+    for a in w:
+        for i in a:
+            cnt[i] += 1
+    assert cnt == [2] * 16 + [1] * 4 + [2] * 4 + [1] * 16 + [2] * 4 + [1] * 4
+    assert O.uniform_windows(0, 24, 24, 1, 4) == [list(range(24))]
+
+
+def test_ddim_known_answers():
+    s = O.DDIM()
+    ts = s.set_timesteps(25)
+    assert ts.tolist()[:3] == [999, 959, 919] and ts.tolist()[-1] == 39 and len(ts) == 25
+    assert float(s.alphas_cumprod[999]) == 0.0  # zero terminal SNR
+    x, v = torch.randn(2, 4, 3, 8, 8), torch.randn(2, 4, 3, 8, 8)
+    # at t=999 (alpha_bar=0): x0 = -v, eps = x
+    out = s.step(v, 999, x)
+    ap = s.alphas_cumprod[959]
+    assert torch.allclose(out, ap.sqrt() * (-v) + (1 - ap).sqrt() * x, atol=1e-6)
+
+
+def test_plucker_golden():
+    g = load("plucker.pt")
+    y = O.plucker_embedding(g["rows"], 0, list(range(1, 9)), tuple(g["img_size"]))
+    assert torch.allclose(y, g["y"].float(), atol=2e-3)
+    assert y.shape == (1, 8, 6, 64, 48)
+
+
+def test_timestep_embedding_layout():
+    e = O.timestep_sincos(torch.tensor([0, 5]), 320)
+    assert torch.allclose(e[0, :160], torch.ones(160)) and torch.allclose(e[0, 160:], torch.zeros(160))  # [cos | sin]
