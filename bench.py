@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- denoising-UNet frames/sec at BASELINE config 2 (one clip: 24 frames of 768x576, CFG batch 2, fp16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--banks 0|1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one per-timestep pass of the hot path for one clip: UNet3DConditionModel.forward on (2,4,24,96,72) latents
+(CFG-doubled), encoder_hidden_states (2,1,768) and pose_cond_fea (2,320,24,96,72).  value = clips * 24 frames / t_step.
+
+  native arm     humanvid_b200 (hand-written sm_100a CUDA through the C ABI).  `value`: inputs resident in HBM, device
+                 time (CUDA events) of K back-to-back forwards.  `e2e`: the public Python call with the step's latents
+                 copied from pinned host memory and the prediction read back to the host every step.
+  reference arm  (--impl reference) the reference-equivalent PyTorch path (the oracle; the reference itself cannot be
+                 imported: diffusers is not installed) in fp32 on the host CPU cores, on a bounded sample of the same
+                 workload: 2 of the 48 frame-passes at full 96x72 latent resolution (all spatial work is per frame; the
+                 temporal attention over 2 instead of 24 frames is 0.2 % of the FLOPs), scaled linearly in frames.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F, H, W = 24, 96, 72
+CH = (320, 640, 1280, 1280)
+XDIM = 768
+FLOPS_CFG2 = 96.30e12   # algorithmic 2*MAC per UNet forward, no bank
+FLOPS_CFG3 = 105.71e12  # with the 16 reference banks
+MM_KW = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+             temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1421.9), d.get("bf16_tflops", 1668.4), d.get("hbm_gbs", 6586.4), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+def synthetic_init_(module, seed, device):
+    """Seeded variance-controlled random init written straight on the device (no checkpoints exist offline; the
+    reference's zero-inits are overridden so every branch does real work)."""
+    import math
+
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in sorted(module.named_parameters()):
+            if p.ndim >= 2:
+                std = 1.0 / math.sqrt(p[0].numel())
+                if any(k in name for k in ("conv2.", "to_out.0.", "ff.net.2.", "proj_out.", "block2.", "zero_conv")):
+                    std *= 0.5
+                p.copy_((torch.randn(p.shape, generator=g, device=device) * std).to(p.dtype))
+            elif name.endswith("bias"):
+                p.copy_((torch.randn(p.shape, generator=g, device=device) * 0.02).to(p.dtype))
+            else:
+                p.copy_((1.0 + 0.1 * torch.randn(p.shape, generator=g, device=device)).to(p.dtype))
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop = gpu_index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_sample(steps, warmup, frames=2):
+    """Oracle (reference-equivalent PyTorch, fp32) on the host cores: UNet forward on `frames` frame-passes per CFG half."""
+    import torch
+
+    from oracle import hv_oracle as O
+
+    nthreads = os.cpu_count() or 1
+    torch.set_num_threads(nthreads)
+    m = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval()
+    synthetic_init_(m, 7, "cpu")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, frames, H, W, generator=g)
+    ehs = torch.randn(2, 1, XDIM, generator=g)
+    pose = torch.randn(2, CH[0], frames, H, W, generator=g) * 0.5
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            m(x, torch.tensor(500), ehs, pose_cond_fea=pose)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    t = sum(times) / len(times)
+    return {"frames_per_s": frames / t, "s_per_sample": t, "cores": nthreads,
+            "sample": f"UNet forward on {frames} of 24 frames x CFG batch 2 at full 96x72 latent (={2 * frames} of 48 frame-passes), fp32, "
+                      f"{nthreads} threads; frames/s = {frames} / t"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_reference_sample(max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
+    line = {"metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": r["frames_per_s"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 24 / r["frames_per_s"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "config2: 1 clip x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D 1.31B params, no reference bank",
+                       "note": "reference = oracle restatement of the reference PyTorch path on host CPU (diffusers not installable offline)"},
+            "cpu_baseline": {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args, rank, world, local_rank):
+    import ctypes as C
+
+    import torch
+
+    import humanvid_b200 as hv
+    from humanvid_b200 import _native as N
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    unet = hv.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM, use_motion_module=True, use_inflated_groupnorm=True,
+                                   motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True, motion_module_type="Vanilla",
+                                   motion_module_kwargs=MM_KW, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    unet = unet.to(dev, torch.float16)
+    synthetic_init_(unet, 7, dev)
+    unet.refresh_native()
+
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    B = 2
+    sample = torch.randn(B, 4, F, H, W, generator=g, device=dev).half()
+    ehs = torch.randn(B, 1, XDIM, generator=g, device=dev).half()
+    ehs[:1] = 0
+    pose = (torch.randn(B, CH[0], F, H, W, generator=g, device=dev) * 0.5).half()
+    flops = FLOPS_CFG2
+    if args.banks:
+        hv.ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
+        lv = {320: H * W, 640: (H // 2) * (W // 2), 1280: (H // 4) * (W // 4)}
+        names = {id(m): n for n, m in unet.named_modules()}
+        for blk in unet.reader_blocks():
+            c = blk.norm1.normalized_shape[0]
+            L = (H // 8) * (W // 8) if names[id(blk)].startswith("mid_block") else lv[c]
+            blk.bank = [torch.randn(B, L, c, generator=g, device=dev).half()]
+        flops = FLOPS_CFG3
+
+    def step():
+        return unet(sample, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    if not torch.isfinite(out).all():
+        raise RuntimeError("non-finite UNet output")
+    launches = unet.last_launch_count
+
+    # ---- kernel-only: inputs resident, K forwards bracketed by barrier + synchronize, device-timed
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        if world > 1:
+            import torch.distributed as dist
+
+            gathered = torch.empty((world, *out.shape[1:]), device=dev, dtype=out.dtype)
+            dist.all_gather_into_tensor(gathered, out[1:2].contiguous())  # reassemble the clips' latents-sized predictions
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = cs.summary()
+
+    # ---- end to end: the step's latents come from pinned host memory, the prediction goes back to the host
+    h_in = torch.empty(sample.shape, dtype=torch.float16).pin_memory()
+    h_in.copy_(sample.cpu())
+    h_out = torch.empty(out.shape, dtype=torch.float16).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d_in = h_in.to(dev, non_blocking=True)
+        o = unet(d_in, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
+        h_out.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / args.steps
+
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    # ---- per-operator device time of one more forward (events around every launch) -> roofline of the dominant kernel
+    lib = N.lib()
+    lib.hv_set_profiling(unet._handle, 1)
+    step()
+    cat_ms, cat_fl, cat_n = (C.c_double * 6)(), (C.c_double * 6)(), (C.c_int64 * 6)()
+    N.check(lib.hv_get_profile(unet._handle, cat_ms, cat_fl, cat_n, 6), unet._handle)
+    lib.hv_set_profiling(unet._handle, 0)
+    names = ["tcgen05_gemm_linear", "tcgen05_implicit_gemm_conv3x3", "tcgen05_spatial_attention", "temporal_attention", "norms", "small_linear"]
+    prof = {names[i]: {"ms": round(cat_ms[i], 3), "tflop": round(cat_fl[i] / 1e12, 3), "launches": int(cat_n[i]),
+                       "tflops": round(cat_fl[i] / 1e9 / cat_ms[i], 1) if cat_ms[i] > 0 else None} for i in range(6)}
+    sustained, burst, hbm, src = peaks()
+    gemm_ms, gemm_fl = cat_ms[0] + cat_ms[1], cat_fl[0] + cat_fl[1]
+    gemm_n = int(cat_n[0] + cat_n[1])
+    achieved = gemm_fl / 1e9 / gemm_ms if gemm_ms > 0 else 0.0
+
+    cpu = cpu_reference_sample(2, 1) if not args.no_cpu_baseline else None
+    value = world * F / (ms / 1000.0)
+    line = {
+        "metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic", "impl": "native",
+        "config": {"workload": ("config3" if args.banks else "config2") + ": 1 clip/GPU x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D "
+                   "1.31B params" + (", 16 reference K/V banks" if args.banks else ", no reference bank"),
+                   "global_batch_clips": world, "parallelism": f"clip-per-gpu x{world}" + (", final all_gather of predictions" if world > 1 else ""),
+                   "l2": "working set per step (2.6 GB weights + multi-GB activations) >> 126 MB L2, no flush needed",
+                   "cond_features": "pose_cond_fea resident (step-invariant; hoisted out of the step as the pipeline's feature cache does)"},
+        "tflops_per_step": flops / 1e12, "achieved_tflops": world and flops / 1e9 / ms,
+        "frac_of_tensor_roofline_sustained": flops / 1e9 / ms / sustained,
+        "e2e": {"value": world * F / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 2),
+                "d2h_bytes_per_step": int(h_out.numel() * 2), "api": "humanvid_b200.UNet3DConditionModel.forward (host latents -> host prediction)"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<128|256> (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
+                     "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_tflop_per_step": gemm_fl / 1e12,
+                     "traffic": None},
+        "op_profile": prof,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--banks", type=int, default=0, help="1 = config 3 (reference K/V banks on)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,10 @@ int hv_op_conv3x3_direct(const void* X, const void* W, const void* bias, void* o
      "hv_op_conv3x3_direct");
 }
 
+size_t hv_groupnorm_scratch_floats(int64_t C, int64_t NF, int64_t HW, int32_t groups) {
+  return groupnorm_scratch_floats((int)C, (int)NF, (int)HW, groups, device_sms() ? device_sms() : 148);
+}
+
 int hv_op_groupnorm(const void* X, int64_t C1, const void* X2, int64_t C2, const void* gamma, const void* beta, void* out,
                     int64_t NF, int64_t HW, int32_t groups, float eps, int32_t silu, float* stats, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;

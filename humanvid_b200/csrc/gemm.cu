@@ -27,10 +27,10 @@ constexpr int GEMM_THREADS = 192;
 
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;  // 48 KB (N=256), 36 KB (N=160), 32 KB (N=128) per stage
   static constexpr int kBTileBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = A_TILE_BYTES + kBTileBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kTmemCols = 2 * BLOCK_N <= 256 ? 256 : 512;  // two accumulator stages, power-of-two allocation
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
 };
@@ -347,6 +347,14 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
       attr_set = true;
     }
     gemm_kernel<256><<<grid, GEMM_THREADS, Cfg<256>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  } else if (block_n == 160) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      err = cudaFuncSetAttribute(gemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<160>::kSmemBytes);
+      if (err != cudaSuccess) return err;
+      attr_set = true;
+    }
+    gemm_kernel<160><<<grid, GEMM_THREADS, Cfg<160>::kSmemBytes, stream>>>(a0, a1, b, p, e);
   } else if (block_n == 128) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -42,7 +42,7 @@ struct GemmProblem {
 
 // C[M, N] = A[M, K] * B[N, K]^T  (fp16 in, fp32 accumulate in TMEM, fused epilogue, fp16 out).
 // a0/a1: TMA maps of the A operand (see make_* helpers in tma.h), b: TMA map of the packed weights [N][K].
-// block_n must be 128 or 256 (256 required for geglu).
+// block_n must be 128, 160 or 256 (256 required for geglu); 160 = two exact tiles for the 320-wide layers.
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
                         const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream);
 

@@ -166,6 +166,30 @@ struct hv_model {
   void* private_ws = nullptr;
   size_t private_ws_bytes = 0;
   int64_t launches = 0;
+  // optional per-category device timing (bench.py's roofline): events bracket every operator launch
+  enum Cat { CAT_GEMM = 0, CAT_CONV = 1, CAT_ATTN = 2, CAT_TATTN = 3, CAT_NORM = 4, CAT_MISC = 5, CAT_N = 6 };
+  bool profiling = false;
+  struct Rec { int cat; cudaEvent_t a, b; double flops; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  cudaEvent_t ev() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      ck(cudaEventCreate(&e), "cudaEventCreate");
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
+  struct Timed {  // RAII bracket around one operator
+    hv_model* m; int cat; double flops; cudaEvent_t a{};
+    Timed(hv_model* mm, int c, double f) : m(mm), cat(c), flops(f) {
+      if (m->profiling && !m->ar.dry) { a = m->ev(); cudaEventRecord(a, m->st); }
+    }
+    ~Timed() {
+      if (m->profiling && !m->ar.dry) { cudaEvent_t b = m->ev(); cudaEventRecord(b, m->st); m->recs.push_back({cat, a, b, flops}); }
+    }
+  };
 
   // ---- UNet
   ConvDirect conv_in;
@@ -191,6 +215,7 @@ struct hv_model {
   ~hv_model() {
     for (void* p : owned) cudaFree(p);
     if (private_ws) cudaFree(private_ws);
+    for (auto e : ev_pool) cudaEventDestroy(e);
   }
 
   // ================================================================== weight helpers
@@ -235,7 +260,7 @@ struct hv_model {
     if (bias) l.bias = vec(pfx + ".bias", out);
     return l;
   }
-  Conv3 conv3(const std::string& pfx, int cout, int cin, bool bias = true) {
+  Conv3 conv3(const std::string& pfx, int cout, int cin, bool bias = true, bool pad_out_64 = false) {
     const Raw& r = get(pfx + ".weight");
     if (r.shape.size() != 4 || r.shape[0] != cout || r.shape[1] != cin || r.shape[2] != 3 || r.shape[3] != 3)
       fail(HV_ERR_INVALID, "weight '%s.weight' is not (%d,%d,3,3)", pfx.c_str(), cout, cin);
@@ -243,7 +268,7 @@ struct hv_model {
     c.cin = cin;
     c.cout = cout;
     c.cin_pad = static_cast<int>(rup(cin, 64));
-    c.cout_pad = cout % 64 == 0 ? cout : static_cast<int>(cout < 64 ? rup(cout, 8) : rup(cout, 64));
+    c.cout_pad = static_cast<int>(pad_out_64 ? rup(cout, 64) : rup(cout, 8));  // pad_out_64: the output feeds another implicit-GEMM conv
     c.w.rows = c.cout_pad;
     c.w.cols = 9LL * c.cin_pad;
     c.w.p = dmalloc(c.w.rows * c.w.cols);
@@ -404,9 +429,9 @@ struct hv_model {
     pg_convs.clear();
     pg_strides.clear();
     for (int i = 0; i < 3; ++i) {
-      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i), bc[i], bc[i]));
+      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i), bc[i], bc[i], true, true));
       pg_strides.push_back(1);
-      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i + 1), bc[i + 1], bc[i]));
+      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i + 1), bc[i + 1], bc[i], true, true));
       pg_strides.push_back(2);
     }
     pg_convs.push_back(conv3("conv_out", cfg.pg_out_channels, bc[3]));
@@ -449,9 +474,10 @@ struct hv_model {
     const int C2 = x2 ? x2->C : 0;
     if (n.C != x.C + C2) fail(HV_ERR_INVALID, "groupnorm width %d != %d + %d", n.C, x.C, C2);
     Tens out = alloc_act(x.NF, x.H, x.W, x.C + C2);
-    float* stats = static_cast<float*>(ar.alloc(sizeof(float) * 2 * x.NF * cfg.norm_groups));
+    float* stats = static_cast<float*>(ar.alloc(sizeof(float) * groupnorm_scratch_floats(x.C + C2, x.NF, x.H * x.W, cfg.norm_groups, sms)));
     if (ar.dry) return out;
     launches += 3;
+    Timed tm(this, CAT_NORM, 0);
     ck(launch_groupnorm(x.p, x.C, x2 ? x2->p : nullptr, C2, n.g, n.b, out.p, x.NF, x.H * x.W, cfg.norm_groups, n.eps, silu ? 1 : 0, stats, sms, st),
        "groupnorm");
     return out;
@@ -462,6 +488,7 @@ struct hv_model {
     if (pre_add && x_new) *x_new = alloc_act(x.NF, x.H, x.W, x.C);
     if (ar.dry) return out;
     launches += 1;
+    Timed tm(this, CAT_NORM, 0);
     ck(launch_layernorm(x.p, n.g, n.b, out.p, x.rows(), x.C, n.eps, pre_add, rows_per_b, (pre_add && x_new) ? x_new->p : nullptr, pe, x.H * x.W, F, st),
        "layernorm");
     return out;
@@ -470,6 +497,7 @@ struct hv_model {
             const hv_epilogue* ep) {
     if (ar.dry) return;
     launches += 1;
+    Timed tm(this, CAT_GEMM, 2.0 * M * w.rows * w.cols);
     ckop(op_gemm(A, lda, A2, lda2, K1, w.p, out, ldc, M, w.rows, w.cols, ep, st), "gemm");
   }
   // y = x W^T + b (+ residual)
@@ -498,6 +526,7 @@ struct hv_model {
     ep.act = act;
     if (residual) { ep.residual = residual->p; ep.ldr = residual->C; }
     launches += 1;
+    Timed tm(this, CAT_CONV, 2.0 * out.rows() * c.cout * 9.0 * c.cin);
     ckop(op_conv3x3(x.p, c.w.p, out.p, c.cout_pad, x.NF, x.H, x.W, c.cin_pad, c.cout_pad, stride, &ep, st), "conv3x3");
     return out;
   }
@@ -505,6 +534,7 @@ struct hv_model {
     __half* out = alloc_h(static_cast<int64_t>(M) * l.w.rows);
     if (ar.dry) return out;
     launches += 1;
+    Timed tm(this, CAT_MISC, 2.0 * M * l.w.rows * l.w.cols);
     ck(launch_small_linear(x, l.w.p, l.bias, out, M, static_cast<int>(l.w.rows), static_cast<int>(l.w.cols), act_in, st), "small_linear");
     return out;
   }
@@ -539,6 +569,7 @@ struct hv_model {
       ep.residual = res.p;
       ep.ldr = res.C;
       launches += 1;
+      Timed tm(this, CAT_CONV, 2.0 * x.rows() * r.cout * 9.0 * r.cout);
       ckop(op_conv3x3(h2.p, r.c2.w.p, out.p, r.cout, x.NF, x.H, x.W, r.c2.cin_pad, r.c2.cout_pad, 1, &ep, st), "resnet conv2");
     }
     return out;
@@ -565,6 +596,7 @@ struct hv_model {
       // V^T[C][frame n: n*Lp + j] = Wv [C][C] * n1^T : weights are the "A" operand, activations the batched "B" operand
       if (!ar.dry) {
         launches += 1;
+        Timed tm(this, CAT_GEMM, 2.0 * tokens * C * C);
         ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, C, x.NF, L, Lp, C, st), "V^T gemm");
       }
       const bool use_bank = w.bank != nullptr;
@@ -580,6 +612,7 @@ struct hv_model {
         vbt = alloc_h(static_cast<int64_t>(C) * ldvbt);
         if (!ar.dry) {
           launches += 1;
+          Timed tm(this, CAT_GEMM, 2.0 * bt * C * C);
           ckop(op_gemm_batched_b(w.wv.p, C, w.bank, C, vbt, ldvbt, C, w.bank_B, w.bank_L, Lbp, C, st), "bank V^T gemm");
         }
       }
@@ -593,6 +626,8 @@ struct hv_model {
         a.F = F; a.nf_nobank = cfg_split ? (B / 2) * F : 0;
         a.vt_stride = Lp; a.vbt_stride = Lbp;
         launches += 1;
+        const double nb_frames = x.NF - a.nf_nobank;
+        Timed tm(this, CAT_ATTN, 4.0 * L * w.C * (static_cast<double>(x.NF) * L + nb_frames * a.Lb));
         cudaError_t e = launch_attention(a, sms, st);
         if (e != cudaSuccess) fail(HV_ERR_CUDA, "attention (%s): %s %s", w.name.c_str(), cudaGetErrorString(e), tma_last_error());
       }
@@ -631,6 +666,7 @@ struct hv_model {
     Tens o = alloc_act(t.NF, t.H, t.W, C);
     if (!ar.dry) {
       launches += 1;
+      Timed tm(this, CAT_TATTN, 4.0 * t.rows() * F * C);
       ck(launch_temporal_attention(qkv, o.p, B, F, t.H * t.W, heads, d, st), "temporal attention");
     }
     hv_epilogue ep{};
@@ -666,6 +702,7 @@ struct hv_model {
     ar.off = 0;
     ar.peak = 0;
     launches = 0;
+    if (!dry) { recs.clear(); ev_used = 0; }
     if (dry) {
       ar.base = nullptr;
       ar.cap = 0;
@@ -833,6 +870,28 @@ int hv_create(const hv_config* cfg, hv_handle* out) {
 void hv_destroy(hv_handle h) { delete h; }
 const char* hv_last_error(hv_handle h) { return h ? h->err.c_str() : last_error(); }
 int64_t hv_last_launch_count(hv_handle h) { return h ? h->launches : 0; }
+
+int hv_set_profiling(hv_handle h, int32_t enable) {
+  if (!h) return HV_ERR_INVALID;
+  h->profiling = enable != 0;
+  return HV_OK;
+}
+
+int hv_get_profile(hv_handle h, double* ms, double* flops, int64_t* count, int32_t ncat) {
+  if (!h || !ms || !flops || !count) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+    if (!h->recs.empty()) ck(cudaEventSynchronize(h->recs.back().b), "profile sync");
+    for (const auto& r : h->recs) {
+      if (r.cat >= ncat) continue;
+      float t = 0;
+      ck(cudaEventElapsedTime(&t, r.a, r.b), "cudaEventElapsedTime");
+      ms[r.cat] += t;
+      flops[r.cat] += r.flops;
+      count[r.cat] += 1;
+    }
+  });
+}
 
 __global__ void cast_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)

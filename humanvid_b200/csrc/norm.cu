@@ -29,22 +29,21 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return u;
 }
 
-// ---------------------------------------------------------------- GroupNorm statistics
-// grid (slabs, NF); thread = (row lane, 8-channel vector).  stats[n][g] = {sum, sumsq} accumulated with atomics.
+// ---------------------------------------------------------------- GroupNorm statistics (deterministic: no atomics)
+// grid (slabs, NF); thread = (row lane, 8-channel vector).  Each block writes its per-group {sum, sumsq} to
+// partial[n][slab][g]; gn_finalize_kernel adds the slabs in a fixed order -> {mean, rstd}.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int groups,
-                                int rows_per_block, float* __restrict__ stats) {
-  extern __shared__ float sacc[];  // [groups][2]
+                                int rows_per_block, float* __restrict__ partial) {
+  extern __shared__ float sred[];  // [blockDim.x][4][2]
   const int C = C1 + C2, vecs = C / 8, cpg = C / groups;
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int rl = threadIdx.x / vecs, v = threadIdx.x % vecs, rpi = blockDim.x / vecs;
-  if (rl < rpi) {
-    const int c0 = v * 8;
+  const int c0 = v * 8;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  {
     const __half* src;
     int ldc, cc;
     if (c0 < C1) { src = x1; ldc = C1; cc = c0; } else { src = x2; ldc = C2; cc = c0 - C1; }
-    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     const int row_end = min(HW, (blockIdx.x + 1) * rows_per_block);
     for (int r = blockIdx.x * rows_per_block + rl; r < row_end; r += rpi) {
       uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<long long>(n) * HW + r) * ldc + cc));
@@ -56,22 +55,52 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
         q[i] += f[2 * i] * f[2 * i] + f[2 * i + 1] * f[2 * i + 1];
       }
     }
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // channels-per-group is even, so a half2 never straddles two groups
-      const int g = (c0 + 2 * i) / cpg;
-      atomicAdd(&sacc[2 * g], s[i]);
-      atomicAdd(&sacc[2 * g + 1], q[i]);
-    }
+  for (int i = 0; i < 4; ++i) {
+    sred[(threadIdx.x * 4 + i) * 2] = s[i];
+    sred[(threadIdx.x * 4 + i) * 2 + 1] = q[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[static_cast<long long>(n) * groups * 2 + i], sacc[i]);
+  // thread g sums, in a fixed order, every (row lane, half2) slot that belongs to group g (channels-per-group is even,
+  // so a half2 never straddles two groups; the slots of a group are the contiguous half2 range [g*cpg/2, (g+1)*cpg/2))
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x, h0 = g * (cpg / 2), h1 = h0 + cpg / 2;
+    float ss = 0.f, qq = 0.f;
+    for (int r = 0; r < rpi; ++r)
+      for (int hh = h0; hh < h1; ++hh) {
+        const int slot = (r * vecs + hh / 4) * 4 + (hh & 3);
+        ss += sred[slot * 2];
+        qq += sred[slot * 2 + 1];
+      }
+    float* dst = partial + ((static_cast<long long>(n) * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = ss;
+    dst[1] = qq;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int total, int groups, int slabs, float inv_cnt,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * groups + g
+  if (i >= total) return;
+  const int n = i / groups, g = i % groups;
+  float ss = 0.f, qq = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) {
+    const float* p = partial + ((static_cast<long long>(n) * slabs + sl) * groups + g) * 2;
+    ss += p[0];
+    qq += p[1];
+  }
+  const float mean = ss * inv_cnt;
+  const float var = fmaxf(qq * inv_cnt - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
                                 long long total_vecs, int HW, int groups, float eps, int silu, const float* __restrict__ stats) {
   const int C = C1 + C2, vecs = C / 8, cpg = C / groups;
-  const float inv_cnt = 1.f / (static_cast<float>(HW) * cpg);
+  (void)eps;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = i / vecs;
@@ -85,10 +114,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g = (c0 + 2 * k) / cpg;
-      const float sum = stats[(static_cast<long long>(n) * groups + g) * 2], sq = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
-      const float mean = sum * inv_cnt;
-      const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
+      const float mean = stats[(static_cast<long long>(n) * groups + g) * 2], rstd = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         float y = r16((f[2 * k + j] - mean) * rstd * gm[2 * k + j] + bt[2 * k + j]);
@@ -169,23 +195,39 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
 
 }  // namespace
 
+// scratch floats needed by launch_groupnorm: final {mean, rstd} + per-slab partials
+static void gn_plan(int C, int NF, int HW, int num_sms, int* threads, int* slabs, int* rows_per_block) {
+  const int vecs = C / 8;
+  int t = vecs * (vecs >= 256 ? 1 : 256 / vecs);
+  if (t > 1024) t = vecs;
+  int sl = (4 * num_sms + NF - 1) / NF;  // enough blocks to fill the machine ~4x, at least 32 rows per block
+  int rpb = (HW + sl - 1) / sl;
+  if (rpb < 32) rpb = 32;
+  sl = (HW + rpb - 1) / rpb;
+  *threads = t;
+  *slabs = sl;
+  *rows_per_block = rpb;
+}
+size_t groupnorm_scratch_floats(int C, int NF, int HW, int groups, int num_sms) {
+  int t, sl, rpb;
+  gn_plan(C, NF, HW, num_sms, &t, &sl, &rpb);
+  return static_cast<size_t>(2) * NF * groups * (1 + sl);
+}
+
 cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2, const __half* gamma, const __half* beta,
                              __half* out, int NF, int HW, int groups, float eps, int silu, float* stats, int num_sms,
                              cudaStream_t stream) {
   const int C = C1 + C2;
-  if (C % 8 || C1 % 8 || C % groups || ((C / groups) & 1)) return cudaErrorInvalidValue;
+  if (C % 8 || C1 % 8 || C % groups || ((C / groups) & 1) || groups > 32 * 8) return cudaErrorInvalidValue;
   const int vecs = C / 8;
   if (vecs > 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * NF * groups, stream);
-  if (e != cudaSuccess) return e;
-  int threads = vecs * (vecs >= 256 ? 1 : 256 / vecs);
-  if (threads > 1024) threads = vecs;
-  // enough blocks to fill the machine ~4x, at least 32 rows per block
-  int slabs = (4 * num_sms + NF - 1) / NF;
-  int rows_per_block = (HW + slabs - 1) / slabs;
-  if (rows_per_block < 32) rows_per_block = 32;
-  slabs = (HW + rows_per_block - 1) / rows_per_block;
-  gn_stats_kernel<<<dim3(slabs, NF), threads, groups * 2 * sizeof(float), stream>>>(x1, C1, x2, C2, HW, groups, rows_per_block, stats);
+  int threads, slabs, rows_per_block;
+  gn_plan(C, NF, HW, num_sms, &threads, &slabs, &rows_per_block);
+  if (threads < groups) return cudaErrorInvalidValue;
+  float* partial = stats + static_cast<size_t>(2) * NF * groups;
+  gn_stats_kernel<<<dim3(slabs, NF), threads, threads * 8 * sizeof(float), stream>>>(x1, C1, x2, C2, HW, groups, rows_per_block, partial);
+  const int total_g = NF * groups;
+  gn_finalize_kernel<<<(total_g + 127) / 128, 128, 0, stream>>>(partial, stats, total_g, groups, slabs, 1.f / (static_cast<float>(HW) * (C / groups)), eps);
   const long long total = static_cast<long long>(NF) * HW * vecs;
   long long blocks = (total + 255) / 256;
   if (blocks > num_sms * 16LL) blocks = num_sms * 16LL;

@@ -59,13 +59,19 @@ static void fill_epilogue(GemmEpilogue& e, const hv_epilogue* ep, __half* out, i
   }
 }
 
+// Tile width: the candidate that pads N the least (N=320 -> 2 x 160, 640 -> 4 x 160, 384 -> 3 x 128, 1280 -> 5 x 256);
+// ties go to the wider tile (fewer A re-reads, better UMMA smem ratio) unless that leaves SMs idle.
 static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
   if (geglu) return 256;
-  if (N <= 128) return 128;
-  // prefer 256-wide tiles (half the A re-reads, full-rate UMMA) unless that leaves most SMs idle
-  const int64_t t256 = m_tiles * ((N + 255) / 256);
-  if (N % 256 != 0 && N % 256 <= 128 && t256 < 2 * sms) return 128;
-  return t256 >= sms / 2 ? 256 : 128;
+  const int cand[3] = {256, 160, 128};
+  int best = 128;
+  int64_t best_pad = -1;
+  for (int bn : cand) {
+    const int64_t padded = (N + bn - 1) / bn * bn;
+    if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = bn; }
+  }
+  if (best != 128 && m_tiles * ((N + best - 1) / best) < sms && m_tiles * ((N + 127) / 128) > m_tiles * ((N + best - 1) / best)) best = 128;
+  return best;
 }
 
 int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_t K1, const __half* W, __half* out, int64_t ldc,

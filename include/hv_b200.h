@@ -94,6 +94,13 @@ int hv_camera_encoder_forward(hv_handle h, const void* plucker, void* out, int32
 /* Kernel launches issued by the last forward on this handle (bench.py's gpu_launches). */
 int64_t hv_last_launch_count(hv_handle h);
 
+/* Optional per-operator-category device timing of the next forwards (CUDA events around every launch on the caller's
+ * stream).  Categories: 0 tcgen05 GEMM (linear / 1x1), 1 tcgen05 implicit-GEMM 3x3 conv, 2 spatial attention,
+ * 3 temporal attention, 4 GroupNorm/LayerNorm, 5 small linears.  hv_get_profile synchronises on the last event and
+ * returns summed milliseconds, algorithmic FLOPs (2*MAC, unpadded shapes) and launch counts of the LAST forward. */
+int hv_set_profiling(hv_handle h, int32_t enable);
+int hv_get_profile(hv_handle h, double* ms, double* flops, int64_t* count, int32_t ncat);
+
 #ifdef __cplusplus
 }
 #endif

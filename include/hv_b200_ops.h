@@ -79,7 +79,8 @@ int hv_op_conv3x3_direct(const void* X, const void* W, const void* bias, void* o
 
 /* GroupNorm over (H*W, C/groups) per frame, fp32 statistics; optional SiLU; reads the channel concatenation of X
  * (C1 channels) and X2 (C2 channels, may be NULL/0) and writes one (NF, HW, C1+C2) tensor. stats: fp32 scratch
- * of 2*NF*groups floats. */
+ * of hv_groupnorm_scratch_floats(...) floats (per-slab partial sums; the reduction is atomics-free and deterministic). */
+size_t hv_groupnorm_scratch_floats(int64_t C, int64_t NF, int64_t HW, int32_t groups);
 int hv_op_groupnorm(const void* X, int64_t C1, const void* X2, int64_t C2, const void* gamma, const void* beta, void* out,
                     int64_t NF, int64_t HW, int32_t groups, float eps, int32_t silu, float* stats, hv_stream_t stream);
 

@@ -133,7 +133,9 @@ def test_groupnorm(C1, C2, silu):
     Ct = C1 + C2
     gamma, beta = dev(Ct, seed=42) * 0.1 + 1, dev(Ct, seed=43) * 0.1
     out = torch.zeros(NF, HW, Ct, device="cuda", dtype=torch.half)
-    stats = torch.zeros(NF * 32 * 2, device="cuda", dtype=torch.float32)
+    f = lib().hv_groupnorm_scratch_floats
+    f.restype = C.c_size_t
+    stats = torch.zeros(int(f(i64(Ct), i64(NF), i64(HW), i32(32))), device="cuda", dtype=torch.float32)
     check(lib().hv_op_groupnorm(ptr(x1), i64(C1), ptr(x2), i64(C2), ptr(gamma), ptr(beta), ptr(out), i64(NF), i64(HW), i32(32),
                                 C.c_float(1e-5), i32(silu), ptr(stats), stream()))
     xc = torch.cat([x1, x2], -1) if C2 else x1
