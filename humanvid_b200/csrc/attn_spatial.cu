@@ -5,9 +5,11 @@
 // Flash-style, tcgen05: one CTA per (128-query tile, head, frame).
 //   warp 0      TMA producer : Q tile once, then K / V^T tiles of 128 keys through a shared-memory ring
 //   warp 1      MMA issuer   : S = Q K^T (UMMA 128x128xdpad) into TMEM, then PV = P V (UMMA 128 x dpad x 128) into TMEM
-//   warps 2..5  softmax      : one query row per thread: tcgen05.ld S, running max / sum in registers, P (fp16) written
-//                              to shared memory in the 128B-swizzled K-major layout the next UMMA reads, PV tile read back
-//                              from TMEM and accumulated into fp32 registers with the online-softmax rescale
+//   warps 2..5  softmax      : one query row per thread: double-buffered tcgen05.ld of S, one sweep per key tile
+//                              (the max is only checked for growth), p = 2^(s*scale - m), P written to shared memory in the 128B-swizzled K-major layout the
+//                              next UMMA reads.  O stays in TMEM across key tiles (UMMA accumulate); V^T carries a row of
+//                              ones per head so O's extra column IS the softmax denominator; O is rescaled in TMEM
+//                              (tcgen05.ld/st) only when a row max grows by more than 2^8 (lazy rescale).
 // Keys come from two segments: the frame's own L tokens and, for frames of the conditional CFG half, the Lb tokens of
 // the batch item's reference bank -- the reference instead materialises cat([x, bank.repeat(F)]) per frame and
 // recomputes the unconditional half (mutual_self_attention.py:158-186).
@@ -29,20 +31,22 @@ namespace {
 constexpr int ATT_THREADS = 192;
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per tile
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is rescaled only when the row max grows by more than 2^8
 
 template <int D>
 struct ACfg {
-  static constexpr int kDpad = (D + 15) / 16 * 16;
+  static constexpr int kDpad = (D + 15) / 16 * 16;             // Q/K head stride (zero padded)
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;           // V^T rows per head: d values, one row of ones, zero pad
   static constexpr int kKC = (kDpad + 63) / 64;               // 64-column chunks of Q / K rows
   static constexpr int kQBytes = kKC * QT * 128;
   static constexpr int kKBytes = kKC * KT * 128;
-  static constexpr int kVChunk = kDpad * 128;                  // [dpad rows][64 keys]
+  static constexpr int kVChunk = kDv * 128;                    // [dv rows][64 keys]
   static constexpr int kVBytes = 2 * kVChunk;
   static constexpr int kPBytes = 2 * QT * 128;                 // two 64-key chunks
   static constexpr int kStageBytes = kKBytes + kVBytes;
   static constexpr int kStages = (kQBytes + kPBytes + 2 * kStageBytes + 2048 <= 227 * 1024) ? 2 : 1;
   static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 256 + 1024;
-  static constexpr int kTmemCols = (128 + kDpad) <= 256 ? 256 : 512;
+  static constexpr int kTmemCols = (128 + kDv) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = (2 * kSmemBytes <= 227 * 1024 && kTmemCols == 256) ? 2 : 1;
 };
 
@@ -60,7 +64,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
             const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
   using C = ACfg<D>;
-  constexpr int DP = C::kDpad;
+  constexpr int DP = C::kDpad, DV = C::kDv;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -104,7 +108,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;          // 128 columns: S tile
-  const uint32_t tmem_pv = tmem_base + 128;   // DP columns: P V tile
+  const uint32_t tmem_o = tmem_base + 128;    // DV columns: O accumulator (column D = softmax denominator)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -121,19 +125,19 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         const bool self = j < Ts;
         const CUtensorMap* mk = self ? &map_k : &map_kb;
         const CUtensorMap* mv = self ? &map_vt : &map_vbt;
-        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;           // K rows
-        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;  // V^T columns (16B aligned)
+        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;                    // K rows
+        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;   // V^T columns (16B aligned)
 #pragma unroll
         for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
-        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * D);
-        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * D);
+        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DP);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       auto issue_s = [&](int stage) {
         const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
@@ -159,7 +163,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         for (int kk = 0; kk < KT / 16; ++kk) {
           const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
           const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
-          umma_f16_ss(tmem_pv, ad, bd, idesc_pv, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);   // O accumulates across key tiles in TMEM
         }
         umma_commit(bar_pv);
         umma_commit(&bar_kv_empty[stage]);
@@ -172,79 +176,131 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
       }
     }
   } else {
+    // ---------------------------------------------------------------- softmax: one query row per thread
     const int qd = warp & 3;
     const int r = qd * 32 + lane;                 // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    float o[DP];
-#pragma unroll
-    for (int c = 0; c < DP; ++c) o[c] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    float m_used = -INFINITY;                     // the (possibly stale) row max the accumulated O and P are relative to
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
+    const float sc = a.scale_log2;
+
+    // Rescale of this row's O accumulator (and of the P chunks of the current tile already written) when the row max
+    // grows by more than the threshold.  Warp-collective because tcgen05.ld/st are; lanes that do not grow use alpha = 1.
+    auto rescale = [&](float alpha, int chunks_done) {
+#pragma unroll
+      for (int c = 0; c < DV / 16; ++c) {
+        uint32_t t16[16];
+        tmem_ld16(tmem_o + lane_off + c * 16, t16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
+        tmem_st16(tmem_o + lane_off + c * 16, t16);
+      }
+      tmem_st_wait();
+      const __half2 a2 = __float2half2_rn(alpha);
+      for (int cc = 0; cc < chunks_done; ++cc) {
+        uint8_t* chunk = prow + (cc >> 1) * (QT * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4* ptr = reinterpret_cast<uint4*>(chunk + ((((cc & 1) * 4 + u) ^ sw) << 4));
+          uint4 v = *ptr;
+          __half2* hp = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hp[i] = __hmul2(hp[i], a2);
+          *ptr = v;
+        }
+      }
+    };
+
     for (int j = 0; j < T; ++j) {
       const bool self = j < Ts;
       const int kv_valid = self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT);
       mbar_wait(bar_s, j & 1);
+      if (j > 0) mbar_wait(bar_pv, (j - 1) & 1);   // previous P V done: P smem and the O accumulator are ours again
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, raw);
-        tmem_ld_wait();
+      uint32_t raw[2][32];
+      if (j == 0) {
+        // first tile: one extra sweep over S to seed the row max (later tiles only check for growth, chunk by chunk)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        tmem_ld32(tmem_s + lane_off, raw[0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      }
-      const float m_new = fmaxf(m, mx * a.scale_log2);
-      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
-      // pass 2: p = exp2(s*scale - m_new) -> fp16 -> swizzled smem; row sum of the ROUNDED p (what the MMA consumes)
-      float psum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_s + lane_off + c * 32, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < KT / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < KT / 32) tmem_ld32(tmem_s + lane_off + (c + 1) * 32, raw[(c + 1) & 1]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c0 = c * 32 + 2 * i;
-          float p0 = c0 < kv_valid ? fast_exp2(__uint_as_float(raw[2 * i]) * a.scale_log2 - m_new) : 0.f;
-          float p1 = c0 + 1 < kv_valid ? fast_exp2(__uint_as_float(raw[2 * i + 1]) * a.scale_log2 - m_new) : 0.f;
-          __half2 hp = __floats2half2_rn(p0, p1);
-          float2 back = __half22float2(hp);
-          psum += back.x + back.y;
-          pk[i] = *reinterpret_cast<uint32_t*>(&hp);
+          for (int i = 0; i < 32; i += 2) {
+            if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
+            if (c * 32 + i + 1 < kv_valid) mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][i + 1]));
+          }
         }
-        // 32 keys = 4 units of 16 B inside 64-key chunk (c / 2), units (c % 2) * 4 + u
+        m_used = fmaxf(mx0, mx1) * sc;
+      }
+      tmem_ld32(tmem_s + lane_off, raw[0]);
+#pragma unroll
+      for (int c = 0; c < KT / 32; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < KT / 32) tmem_ld32(tmem_s + lane_off + (c + 1) * 32, raw[(c + 1) & 1]);
+        const bool full = (c + 1) * 32 <= kv_valid;
+        if (j > 0) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
+              mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][i + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
+          }
+          const float cm = fmaxf(mx0, mx1) * sc;
+          const bool grow = cm > m_used + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = grow ? cm : m_used;
+            rescale(grow ? fast_exp2(m_used - m_new) : 1.0f, c);
+            m_used = m_new;
+          }
+        }
+        uint32_t pk[16];
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i + 1]), sc, -m_used)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = c * 32 + 2 * i;
+            const float p0 = c0 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i]), sc, -m_used)) : 0.f;       // keys past the
+            const float p1 = c0 + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i + 1]), sc, -m_used)) : 0.f; // segment end: p = 0
+            pk[i] = pack_h2(p0, p1);
+          }
+        }
         uint8_t* chunk = prow + (c >> 1) * (QT * 128);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c & 1) * 4 + u;
-          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(chunk + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
-      l = l * alpha + psum;
-      m = m_new;
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_p);
-      // accumulate this tile's P V
-      mbar_wait(bar_pv, j & 1);
-      tc_fence_after();
+    }
+    // epilogue: O / denominator
+    mbar_wait(bar_pv, (T - 1) & 1);
+    tc_fence_after();
+    float o[DV];
 #pragma unroll
-      for (int c = 0; c < DP / 16; ++c) {
-        uint32_t raw[16];
-        tmem_ld16(tmem_pv + lane_off + c * 16, raw);
-        tmem_ld_wait();
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_o + lane_off + c * 16, raw);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[c * 16 + i] = o[c * 16 + i] * alpha + __uint_as_float(raw[i]);
-      }
+      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw[i]);
     }
     tc_fence_before();
     if (q0 + r < a.L) {
-      const float inv = 1.f / l;
+      const float inv = 1.f / o[D];
       __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
 #pragma unroll
       for (int c = 0; c < D / 8; ++c) {
@@ -273,13 +329,13 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   const long long tokens = static_cast<long long>(a.NF) * a.L;
   if (!make_map_2d(&mq, a.q, tokens, a.ldq, a.ldq, QT)) return cudaErrorInvalidValue;
   if (!make_map_2d(&mk, a.k, tokens, a.ldk, a.ldk, KT)) return cudaErrorInvalidValue;
-  if (!make_map_2d(&mvt, a.vt, static_cast<long long>(a.heads) * D, static_cast<long long>(a.NF) * a.vt_stride, a.ldvt, C::kDpad)) return cudaErrorInvalidValue;
+  if (!make_map_2d(&mvt, a.vt, static_cast<long long>(a.heads) * C::kDv, static_cast<long long>(a.NF) * a.vt_stride, a.ldvt, C::kDv)) return cudaErrorInvalidValue;
   mkb = mk;
   mvbt = mvt;
   const int B = a.NF / (a.F > 0 ? a.F : 1);
   if (a.Lb > 0) {
     if (!make_map_2d(&mkb, a.kb, static_cast<long long>(B) * a.Lb, a.ldkb, a.ldkb, KT)) return cudaErrorInvalidValue;
-    if (!make_map_2d(&mvbt, a.vbt, static_cast<long long>(a.heads) * D, static_cast<long long>(B) * a.vbt_stride, a.ldvbt, C::kDpad))
+    if (!make_map_2d(&mvbt, a.vbt, static_cast<long long>(a.heads) * C::kDv, static_cast<long long>(B) * a.vbt_stride, a.ldvbt, C::kDv))
       return cudaErrorInvalidValue;
   }
   static bool attr = false;

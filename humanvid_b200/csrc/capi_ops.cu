@@ -28,8 +28,8 @@ int hv_op_gemm(const void* A, int64_t lda, const void* A2, int64_t lda2, int64_t
 }
 
 int hv_op_gemm_batched_b(const void* A, int64_t lda, const void* X, int64_t ldx, void* out, int64_t ldc, int64_t M, int64_t batch,
-                         int64_t rows, int64_t out_stride, int64_t K, hv_stream_t stream) {
-  return op_gemm_batched_b(H(A), lda, H(X), ldx, HM(out), ldc, M, batch, rows, out_stride, K, ST(stream));
+                         int64_t rows, int64_t out_stride, int64_t K, const void* rowbias, hv_stream_t stream) {
+  return op_gemm_batched_b(H(A), lda, H(X), ldx, HM(out), ldc, M, batch, rows, out_stride, K, H(rowbias), ST(stream));
 }
 
 int hv_op_conv3x3(const void* X, const void* Wp, void* out, int64_t ldc, int64_t NF, int64_t Hh, int64_t W, int64_t Cin,
@@ -68,7 +68,7 @@ int hv_op_attention(const void* Q, const void* K, const void* Vt, void* out, int
   if (!device_sms()) return HV_ERR_CUDA;
   AttnArgs a;
   a.q = H(Q); a.k = H(K); a.vt = H(Vt); a.out = HM(out);
-  a.NF = (int)NF; a.L = (int)L; a.heads = heads; a.d = d; a.dpad = (d + 15) / 16 * 16;
+  a.NF = (int)NF; a.L = (int)L; a.heads = heads; a.d = d; a.dpad = (d + 15) / 16 * 16;  // V^T rows per head: (d + 1 + 15) / 16 * 16, row d of every head = ones
   a.ldq = ldq; a.ldk = ldk; a.ldvt = ldvt; a.ldo = ldo;
   a.kb = H(Kb); a.vbt = H(Vbt); a.Lb = Kb ? (int)Lb : 0; a.ldkb = ldkb; a.ldvbt = ldvbt;
   a.F = (int)F; a.nf_nobank = (int)nf_nobank; a.vt_stride = vt_stride; a.vbt_stride = vbt_stride;

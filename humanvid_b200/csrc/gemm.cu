@@ -7,8 +7,9 @@
 //                               (BLOCK_N rows x 64 k) into a ring of 128B-swizzled shared-memory stages
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), accumulators
 //                               double-buffered in TMEM (2 x BLOCK_N columns); owns TMEM alloc/dealloc
-//   warps 2..5  epilogue      : tcgen05.ld of the accumulator (one output row per thread), bias / time-embedding
-//                               row vector / activation / GEGLU / residual, fp16 store
+//   warps 2..9  epilogue      : tcgen05.ld of the accumulator (one output row per thread, two warps per TMEM lane
+//                               quadrant splitting the columns), bias / time-embedding row vector / activation /
+//                               GEGLU / residual, fp16 store
 // The A operand is addressed through TMA only, so a 3x3 convolution over a channels-last (N,H,W,C) tensor is the
 // same kernel: k-block kb = (tap, 64-channel block) and the tile of 128 output pixels is a (bn x bh x bw) box whose
 // input window is fetched with the box shifted by the tap offset; TMA's out-of-bounds zero fill is the padding.
@@ -23,7 +24,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BLOCK_N>
 struct Cfg {
@@ -106,7 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
-      mbar_init(&bar_tempty[s], 4);
+      mbar_init(&bar_tempty[s], 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&map_a0);
@@ -185,12 +186,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, 1 output row / thread)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------------ epilogue (8 warps, 1 output row / thread)
+    // Two warps share each TMEM lane quadrant and split the tile's columns.  TMEM loads are double-buffered against
+    // the math of the previous chunk and the residual row is prefetched one chunk ahead (before the accumulator is
+    // even ready for chunk 0), so neither the TMEM nor the global-load latency sits on the critical path.
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int hsel = (warp - 2) >> 2;  // which half of the tile's columns
     const int r = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int kOutCols = BLOCK_N;  // per tile; geglu writes BLOCK_N/2
+    constexpr int HALF = BLOCK_N / 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const TileCoord tc = tile_coord(p, m_blk);
@@ -206,88 +211,122 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         row_ok = n < p.NF && y < p.H && x < p.W;
         row = (static_cast<long long>(n) * p.H + y) * p.W + x;
       }
-      const __half* rv = nullptr;
-      if (e.rowvec != nullptr && row_ok) rv = e.rowvec + (row / e.rows_per_group) * e.rowvec_ld;
-      const __half* res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
-      __half* out = e.out + row * e.ldc;
-
-      mbar_wait(&bar_tfull[acc], acc_phase);
-      tc_fence_after();
+      const __half* __restrict__ rv = (e.rowvec != nullptr && row_ok) ? e.rowvec + (row / e.rows_per_group) * e.rowvec_ld : nullptr;
+      const __half* __restrict__ res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
+      const __half* __restrict__ bias = e.bias;
+      const float rowbias = (e.rowbias != nullptr && row_ok) ? __half2float(e.rowbias[row]) : 0.f;
+      __half* __restrict__ out = e.out + row * e.ldc;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 
       if (!e.geglu) {
-#pragma unroll 1
-        for (int c = 0; c < kOutCols / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(t_acc + c * 32, raw);
+        constexpr int CW = (HALF % 32 == 0) ? 32 : 16;
+        constexpr int NC = HALF / CW;
+        const int tile_col0 = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + (n_blk % n_per_batch) * BLOCK_N : n_blk * BLOCK_N;
+        const int col_lim = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + ((p.b_rows + 7) & ~7) : e.n_valid;
+        const int colbase = tile_col0 + hsel * HALF;
+        uint32_t raw[2][CW];
+        uint4 rres[2][CW / 8];
+        auto fetch_res = [&](int c, int buf) {
+#pragma unroll
+          for (int g = 0; g < CW / 8; ++g) {
+            const int col = colbase + c * CW + g * 8;
+            rres[buf][g] = (res != nullptr && col < col_lim) ? __ldg(reinterpret_cast<const uint4*>(res + col)) : make_uint4(0, 0, 0, 0);
+          }
+        };
+        auto fetch_acc = [&](int c, int buf) {
+          if constexpr (CW == 32) tmem_ld32(t_acc + hsel * HALF + c * CW, raw[buf]);
+          else tmem_ld16(t_acc + hsel * HALF + c * CW, raw[buf]);
+        };
+        fetch_res(0, 0);
+        mbar_wait(&bar_tfull[acc], acc_phase);
+        tc_fence_after();
+        fetch_acc(0, 0);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
           tmem_ld_wait();
-          const int col0 = (p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + (n_blk % n_per_batch) * BLOCK_N : n_blk * BLOCK_N) + c * 32;
-          const int col_lim = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + ((p.b_rows + 7) & ~7) : e.n_valid;
+          if (c + 1 < NC) {
+            fetch_acc(c + 1, (c + 1) & 1);
+            fetch_res(c + 1, (c + 1) & 1);
+          }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= col_lim) break;
-            float v[8], t[8];
+          for (int g = 0; g < CW / 8; ++g) {
+            const int col = colbase + c * CW + g * 8;
+            if (col < col_lim) {
+              float v[8], t[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]);
-            if (e.bias != nullptr) {
-              load8(e.bias + col, t);
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
+              if (bias != nullptr) {
+                load8(bias + col, t);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += t[i];
+                for (int i = 0; i < 8; ++i) v[i] += t[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
+              if (rv != nullptr) {
+                load8(rv + col, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+              }
+              if (e.act == ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+              } else if (e.act == ACT_SILU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
+              }
+              if (res != nullptr) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rres[c & 1][g]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __half22float2(h2[i]);
+                  v[2 * i] += f.x;
+                  v[2 * i + 1] += f.y;
+                }
+              }
+              if (row_ok) store8(out + col, v);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
-            if (rv != nullptr) {
-              load8(rv + col, t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
-            }
-            if (e.act == ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-            } else if (e.act == ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
-            }
-            if (res != nullptr) {
-              load8(res + col, t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = v[i] + t[i];
-            }
-            if (row_ok) store8(out + col, v);
           }
         }
       } else {
-        // GEGLU: columns [0,128) of the tile are "hidden", [128,256) the matching "gate" rows of the packed weight.
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
-          uint32_t hraw[32], graw[32];
-          tmem_ld32(t_acc + c * 32, hraw);
-          tmem_ld32(t_acc + BLOCK_N / 2 + c * 32, graw);
+        // GEGLU (BLOCK_N == 256): tile columns [0,128) are "hidden", [128,256) the matching "gate" rows of the packed
+        // weight; this warp-half owns hidden columns [hsel*64, hsel*64+64) and their gates.
+        constexpr int CW = 16, NC = (BLOCK_N / 4) / CW;
+        const int hcol0 = hsel * (BLOCK_N / 4);
+        uint32_t hraw[2][CW], graw[2][CW];
+        auto fetch_acc = [&](int c, int buf) {
+          tmem_ld16(t_acc + hcol0 + c * CW, hraw[buf]);
+          tmem_ld16(t_acc + BLOCK_N / 2 + hcol0 + c * CW, graw[buf]);
+        };
+        mbar_wait(&bar_tfull[acc], acc_phase);
+        tc_fence_after();
+        fetch_acc(0, 0);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
           tmem_ld_wait();
-          const int pcol0 = n_blk * BLOCK_N + c * 32;          // packed column of the hidden part
-          const int ocol0 = n_blk * (BLOCK_N / 2) + c * 32;    // output column
+          if (c + 1 < NC) fetch_acc(c + 1, (c + 1) & 1);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int ocol = ocol0 + g * 8;
-            if (ocol >= e.n_valid) break;
-            float hv[8], gv[8], t[8];
+          for (int g = 0; g < CW / 8; ++g) {
+            const int pcol = n_blk * BLOCK_N + hcol0 + c * CW + g * 8;                // packed column of the hidden part
+            const int ocol = n_blk * (BLOCK_N / 2) + hcol0 + c * CW + g * 8;          // output column
+            if (ocol < e.n_valid) {
+              float hv[8], gv[8], t[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              hv[i] = __uint_as_float(hraw[g * 8 + i]);
-              gv[i] = __uint_as_float(graw[g * 8 + i]);
+              for (int i = 0; i < 8; ++i) {
+                hv[i] = __uint_as_float(hraw[c & 1][g * 8 + i]);
+                gv[i] = __uint_as_float(graw[c & 1][g * 8 + i]);
+              }
+              if (bias != nullptr) {
+                load8(bias + pcol, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hv[i] += t[i];
+                load8(bias + pcol + BLOCK_N / 2, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gv[i] += t[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hv[i] = r16(hv[i]) * r16(gelu_erf_f(r16(gv[i])));
+              if (row_ok) store8(out + ocol, hv);
             }
-            if (e.bias != nullptr) {
-              load8(e.bias + pcol0 + g * 8, t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) hv[i] += t[i];
-              load8(e.bias + pcol0 + BLOCK_N / 2 + g * 8, t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) gv[i] += t[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hv[i] = r16(hv[i]) * r16(gelu_erf_f(r16(gv[i])));
-            if (row_ok) store8(out + ocol, hv);
           }
         }
       }

@@ -100,7 +100,9 @@ struct SpatialW {
   Lin proj_in, proj_out;
   Mat wqk;   // [2*heads*dpad][C]  (q rows then k rows, each head zero-padded to dpad)
   Mat wk;    // [heads*dpad][C]    view into wqk (bank keys)
-  Mat wv;    // [C][C]
+  Mat wv;    // [heads*dv][C]: to_v rows of head h at h*dv.., zero rows elsewhere (dv = (d+1) rounded up to 16)
+  __half* vones = nullptr;  // [heads*dv]: 1 at row h*dv + d (the softmax-denominator row of V^T), else 0
+  int dv = 0;
   Lin out1;
   Lin v2, out2;  // cross-attention collapse: to_v (C x xdim), to_out
   Lin ff1, ff2;  // ff1 geglu-packed
@@ -329,7 +331,16 @@ struct hv_model {
     ck(launch_pack_heads(mat(b + ".attn1.to_q.weight", C, C).p, s.wqk.p, s.heads, s.d, s.dpad, C, sms, st), "pack q");
     ck(launch_pack_heads(mat(b + ".attn1.to_k.weight", C, C).p, s.wqk.p + hp * C, s.heads, s.d, s.dpad, C, sms, st), "pack k");
     s.wk = Mat{s.wqk.p + hp * C, hp, C};
-    s.wv = mat(b + ".attn1.to_v.weight", C, C);
+    s.dv = static_cast<int>(rup(s.d + 1, 16));
+    s.wv = Mat{dmalloc(static_cast<int64_t>(s.heads) * s.dv * C), static_cast<int64_t>(s.heads) * s.dv, C};
+    ck(launch_pack_heads(mat(b + ".attn1.to_v.weight", C, C).p, s.wv.p, s.heads, s.d, s.dv, C, sms, st), "pack v");
+    {
+      std::vector<__half> ones(static_cast<size_t>(s.heads) * s.dv, __float2half(0.f));
+      for (int hh = 0; hh < s.heads; ++hh) ones[static_cast<size_t>(hh) * s.dv + s.d] = __float2half(1.f);
+      s.vones = dmalloc(static_cast<int64_t>(ones.size()));
+      ck(cudaMemcpyAsync(s.vones, ones.data(), ones.size() * 2, cudaMemcpyHostToDevice, st), "vones upload");
+      ck(cudaStreamSynchronize(st), "vones sync");  // `ones` is a host temporary
+    }
     s.out1 = lin(b + ".attn1.to_out.0", C, C);
     s.v2 = lin(b + ".attn2.to_v", C, cfg.cross_attention_dim, false);
     s.out2 = lin(b + ".attn2.to_out.0", C, C);
@@ -592,12 +603,13 @@ struct hv_model {
       __half* qk = alloc_h(tokens * 2 * hp);
       gemm(n1.p, C, nullptr, 0, 0, w.wqk, qk, 2 * hp, tokens, nullptr);
       const int64_t Lp = rup(L, 8), ldvt = static_cast<int64_t>(x.NF) * Lp;
-      __half* vt = alloc_h(static_cast<int64_t>(C) * ldvt);
+      const int64_t vrows = static_cast<int64_t>(w.heads) * w.dv;
+      __half* vt = alloc_h(vrows * ldvt);
       // V^T[C][frame n: n*Lp + j] = Wv [C][C] * n1^T : weights are the "A" operand, activations the batched "B" operand
       if (!ar.dry) {
         launches += 1;
         Timed tm(this, CAT_GEMM, 2.0 * tokens * C * C);
-        ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, C, x.NF, L, Lp, C, st), "V^T gemm");
+        ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, vrows, x.NF, L, Lp, C, w.vones, st), "V^T gemm");
       }
       const bool use_bank = w.bank != nullptr;
       __half *kb = nullptr, *vbt = nullptr;
@@ -609,11 +621,11 @@ struct hv_model {
         gemm(w.bank, C, nullptr, 0, 0, w.wk, kb, hp, bt, nullptr);
         Lbp = rup(w.bank_L, 8);
         ldvbt = w.bank_B * Lbp;
-        vbt = alloc_h(static_cast<int64_t>(C) * ldvbt);
+        vbt = alloc_h(vrows * ldvbt);
         if (!ar.dry) {
           launches += 1;
           Timed tm(this, CAT_GEMM, 2.0 * bt * C * C);
-          ckop(op_gemm_batched_b(w.wv.p, C, w.bank, C, vbt, ldvbt, C, w.bank_B, w.bank_L, Lbp, C, st), "bank V^T gemm");
+          ckop(op_gemm_batched_b(w.wv.p, C, w.bank, C, vbt, ldvbt, vrows, w.bank_B, w.bank_L, Lbp, C, w.vones, st), "bank V^T gemm");
         }
       }
       Tens o = alloc_act(x.NF, x.H, x.W, C);

@@ -115,7 +115,7 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
 }
 
 int op_gemm_batched_b(const __half* A, int64_t lda, const __half* X, int64_t ldx, __half* out, int64_t ldc, int64_t M, int64_t batch,
-                      int64_t rows, int64_t out_stride, int64_t K, cudaStream_t stream) {
+                      int64_t rows, int64_t out_stride, int64_t K, const __half* rowbias, cudaStream_t stream) {
   const int sms = device_sms();
   if (!sms) return HV_ERR_CUDA;
   if (M <= 0 || batch <= 0 || rows <= 0 || (K % 8) || (lda % 8) || (ldx % 8) || (ldc % 8) || (out_stride % 8) || out_stride < rows) {
@@ -140,6 +140,7 @@ int op_gemm_batched_b(const __half* A, int64_t lda, const __half* X, int64_t ldx
   e.out = out;
   e.ldc = static_cast<int>(ldc);
   e.n_valid = static_cast<int>(rows);
+  e.rowbias = rowbias;
   cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream);
   if (err != cudaSuccess) return cuda_fail(err, "hv_op_gemm_batched_b launch");
   return HV_OK;

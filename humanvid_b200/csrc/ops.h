@@ -18,7 +18,7 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
             int64_t M, int64_t N, int64_t K, const hv_epilogue* ep, cudaStream_t stream);
 // out[M][n*out_stride + j] = sum_k A[M][k] * X[n][j][k] for n < batch, j < rows (X: [batch][rows][ldx]); out_stride % 8 == 0.
 int op_gemm_batched_b(const __half* A, int64_t lda, const __half* X, int64_t ldx, __half* out, int64_t ldc, int64_t M, int64_t batch,
-                      int64_t rows, int64_t out_stride, int64_t K, cudaStream_t stream);
+                      int64_t rows, int64_t out_stride, int64_t K, const __half* rowbias, cudaStream_t stream);
 int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin,
                int64_t Cout, int stride, const hv_epilogue* ep, cudaStream_t stream);
 

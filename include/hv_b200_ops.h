@@ -64,7 +64,8 @@ int hv_op_gemm(const void* A, int64_t lda, const void* A2, int64_t lda2, int64_t
 /* out[M][n*out_stride + j] = sum_k A[M][k] * X[n][j][k], n < batch, j < rows: the "swapped" GEMM that yields V^T with every
  * frame's token segment starting on a 16-byte boundary (out_stride % 8 == 0), as TMA readers of V^T require. */
 int hv_op_gemm_batched_b(const void* A, int64_t lda, const void* X, int64_t ldx, void* out, int64_t ldc, int64_t M, int64_t batch,
-                         int64_t rows, int64_t out_stride, int64_t K, hv_stream_t stream);
+                         int64_t rows, int64_t out_stride, int64_t K, const void* rowbias /* fp16 [M] added to row m, or NULL */,
+                         hv_stream_t stream);
 
 /* 3x3 convolution, padding 1, stride 1 or 2, over channels-last X (NF, H, W, Cin) -> out (NF, Ho, Wo, Cout) given as
  * a [rows][ldc] matrix.  Wp is the packed weight [Cout][9 * Cin] with k = (ky*3 + kx) * Cin + c (see hv_pack_conv3x3).
@@ -91,9 +92,11 @@ int hv_op_layernorm(const void* X, const void* gamma, const void* beta, void* ou
                     const void* pre_add, int64_t rows_per_group, void* x_out, const void* pe, int64_t hw, int64_t F,
                     hv_stream_t stream);
 
-/* Spatial multi-head attention.  Q: [NF*L][ldq] (head h at columns h*dpad), K likewise, Vt: [heads*d][ldvt] holding
+/* Spatial multi-head attention.  Q: [NF*L][ldq] (head h at columns h*dpad, dpad = d rounded up to 16, pad columns zero), K
+ * likewise.  Vt: [heads*dv][ldvt], dv = (d+1) rounded up to 16: rows h*dv..h*dv+d-1 = V of head h transposed, row h*dv+d = ONES (its
+ * P*V column is the softmax denominator), remaining rows zero; holding
  * V transposed: frame n's tokens occupy columns [n*vt_stride, n*vt_stride + L), vt_stride % 8 == 0.  Optional bank keys/values per batch item (frame n uses bank n / F):
- * Kb [B][Lb][ldkb], Vbt [heads*d][B*vbt_stride].  Frames with n < nf_nobank attend to their own L keys only (the
+ * Kb [B][Lb][ldkb], Vbt [heads*dv][B*vbt_stride] (same row layout).  Frames with n < nf_nobank attend to their own L keys only (the
  * unconditional CFG half).  out: [NF*L][heads*d]. */
 int hv_op_attention(const void* Q, const void* K, const void* Vt, void* out, int64_t NF, int64_t L, int32_t heads,
                     int32_t d, int64_t ldq, int64_t ldk, int64_t ldvt, int64_t ldo, const void* Kb, const void* Vbt,

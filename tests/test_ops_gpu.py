@@ -194,11 +194,20 @@ def attention_case(NF, L, heads, d, Lb=0, Fr=1, nf_nobank=0, seed=70):
     qk = qk.reshape(NF * L, 2 * heads * dpad)
     Lp = (L + 7) // 8 * 8
     ldvt = NF * Lp
-    vt = torch.zeros(heads * d, NF, Lp, device="cuda", dtype=torch.half)
-    check(lib().hv_op_gemm_batched_b(ptr(torch.eye(heads * d, device="cuda", dtype=torch.half)), i64(heads * d), ptr(v.reshape(NF * L, heads * d)),
-                                     i64(heads * d), ptr(vt), i64(ldvt), i64(heads * d), i64(NF), i64(L), i64(Lp), i64(heads * d), stream()))
+    dv = (d + 1 + 15) // 16 * 16
+    sel = torch.zeros(heads, dv, heads, d, device="cuda", dtype=torch.half)  # row h*dv+c picks channel h*d+c
+    ones = torch.zeros(heads, dv, device="cuda", dtype=torch.half)
+    for hh in range(heads):
+        sel[hh, :d, hh, :] = torch.eye(d, device="cuda", dtype=torch.half)
+        ones[hh, d] = 1
+    sel = sel.reshape(heads * dv, heads * d).contiguous()
+    vt = torch.zeros(heads * dv, NF, Lp, device="cuda", dtype=torch.half)
+    check(lib().hv_op_gemm_batched_b(ptr(sel), i64(heads * d), ptr(v.reshape(NF * L, heads * d)), i64(heads * d), ptr(vt), i64(ldvt),
+                                     i64(heads * dv), i64(NF), i64(L), i64(Lp), i64(heads * d), ptr(ones), stream()))
     torch.cuda.synchronize()
-    assert torch.equal(vt[:, :, :L], v.reshape(NF, L, heads * d).permute(2, 0, 1)), "batched-B GEMM (V^T producer) mismatch"
+    vt4 = vt.reshape(heads, dv, NF, Lp)
+    assert torch.equal(vt4[:, :d, :, :L], v.reshape(NF, L, heads, d).permute(2, 3, 0, 1)), "batched-B GEMM (V^T producer) mismatch"
+    assert torch.equal(vt4[:, d, :, :L], torch.ones_like(vt4[:, d, :, :L]))
     out = torch.zeros(NF * L, heads * d, device="cuda", dtype=torch.half)
     kb = vbt = None
     B = NF // Fr
@@ -209,9 +218,10 @@ def attention_case(NF, L, heads, d, Lb=0, Fr=1, nf_nobank=0, seed=70):
         kb[:, :, :d] = kbr
         kb = kb.reshape(B * Lb, heads * dpad)
         Lbp = (Lb + 7) // 8 * 8
-        vbt = torch.zeros(heads * d, B, Lbp, device="cuda", dtype=torch.half)
-        vbt[:, :, :Lb] = vbr.reshape(B, Lb, heads * d).permute(2, 0, 1)
-        vbt = vbt.reshape(heads * d, B * Lbp)
+        vbt = torch.zeros(heads, dv, B, Lbp, device="cuda", dtype=torch.half)
+        vbt[:, :d, :, :Lb] = vbr.reshape(B, Lb, heads, d).permute(2, 3, 0, 1)
+        vbt[:, d, :, :Lb] = 1
+        vbt = vbt.reshape(heads * dv, B * Lbp)
     k_view = qk[:, heads * dpad:]
     check(lib().hv_op_attention(ptr(qk), C.c_void_p(k_view.data_ptr()), ptr(vt), ptr(out), i64(NF), i64(L), i32(heads), i32(d),
                                 i64(2 * heads * dpad), i64(2 * heads * dpad), i64(ldvt), i64(heads * d), ptr(kb), ptr(vbt), i64(Lb),
