@@ -251,6 +251,8 @@ def run_native(args, rank, world, local_rank):
     step()
     cat_ms, cat_fl, cat_n = (C.c_double * 6)(), (C.c_double * 6)(), (C.c_int64 * 6)()
     N.check(lib.hv_get_profile(unet._handle, cat_ms, cat_fl, cat_n, 6), unet._handle)
+    if os.environ.get("HV_TRACE"):
+        lib.hv_dump_profile(unet._handle, os.environ["HV_TRACE"].encode())
     lib.hv_set_profiling(unet._handle, 0)
     names = ["tcgen05_gemm_linear", "tcgen05_implicit_gemm_conv3x3", "tcgen05_spatial_attention", "temporal_attention", "norms", "small_linear"]
     prof = {names[i]: {"ms": round(cat_ms[i], 3), "tflop": round(cat_fl[i] / 1e12, 3), "launches": int(cat_n[i]),

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -45,7 +46,7 @@ struct ACfg {
   static constexpr int kPBytes = 2 * QT * 128;                 // two 64-key chunks
   static constexpr int kStageBytes = kKBytes + kVBytes;
   static constexpr int kStages = (kQBytes + kPBytes + 2 * kStageBytes + 2048 <= 227 * 1024) ? 2 : 1;
-  static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 128 + 2048 + 1024;  // + barriers, row-max exchange, alignment
   static constexpr int kTmemCols = (128 + kDv) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = (2 * kSmemBytes <= 227 * 1024 && kTmemCols == 256) ? 2 : 1;
 };
@@ -72,12 +73,13 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   uint8_t* sKV = sP + C::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::kStages * C::kStageBytes);
   uint64_t* bar_q = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_pv = bars + 3;
-  uint64_t* bar_kv_full = bars + 4;
-  uint64_t* bar_kv_empty = bars + 4 + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * C::kStages);
+  uint64_t* bar_p = bars + 1;
+  uint64_t* bar_pv = bars + 2;
+  uint64_t* bar_s = bars + 3;        // [2]: S half h (keys 64h..64h+63 of the tile) is in TMEM
+  uint64_t* bar_sfree = bars + 5;    // [2]: the softmax warps have read S half h (128 arrivals)
+  uint64_t* bar_kv_full = bars + 7;
+  uint64_t* bar_kv_empty = bars + 7 + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * C::kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT;
@@ -90,9 +92,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
-    mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_pv, 1);
+    for (int hh = 0; hh < 2; ++hh) {
+      mbar_init(&bar_s[hh], 1);
+      mbar_init(&bar_sfree[hh], 128);
+    }
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&bar_kv_full[s], 1);
       mbar_init(&bar_kv_empty[s], 1);
@@ -136,28 +141,22 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
       constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_s = [&](int stage) {
-        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
+      // S is produced in two 64-key halves (UMMA 128x64xdpad each) so that, with two K/V stages, the next tile's scores
+      // are already in TMEM while the softmax warps still work on the current tile: they never wait for the tensor pipe.
+      constexpr uint32_t idesc_sh = umma_idesc_f16(QT, KT / 2);
+      auto issue_s_half = [&](int stage, int hh) {
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes) + hh * (KT / 2) * 128;
 #pragma unroll
         for (int ks = 0; ks < DP / 16; ++ks) {
           const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
           const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
-          umma_f16_ss(tmem_s, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_s + hh * (KT / 2), ad, bd, idesc_sh, ks != 0 ? 1u : 0u);
         }
-        umma_commit(bar_s);
+        umma_commit(&bar_s[hh]);
       };
-      int stage = 0;
-      uint32_t phase = 0;
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(bar_p, j & 1);
-        tc_fence_after();
+      auto issue_pv = [&](int stage, int j) {
         const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
 #pragma unroll
         for (int kk = 0; kk < KT / 16; ++kk) {
@@ -167,12 +166,45 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         }
         umma_commit(bar_pv);
         umma_commit(&bar_kv_empty[stage]);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-        if (j + 1 < T) {
-          mbar_wait(&bar_kv_full[stage], phase);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv_full[0], 0);
+      tc_fence_after();
+      issue_s_half(0, 0);
+      issue_s_half(0, 1);
+      for (int j = 0; j < T; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == C::kStages) { nstage = 0; nphase ^= 1; }
+        if constexpr (C::kStages >= 2) {
+          if (j + 1 < T) {
+            mbar_wait(&bar_kv_full[nstage], nphase);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              mbar_wait(&bar_sfree[hh], j & 1);
+              tc_fence_after();
+              issue_s_half(nstage, hh);
+            }
+          }
+          mbar_wait(bar_p, j & 1);
           tc_fence_after();
-          issue_s(stage);
+          issue_pv(stage, j);
+        } else {
+          // one K/V stage only (d = 160): the next K tile can only land after this tile's P V released the stage
+          mbar_wait(bar_p, j & 1);
+          tc_fence_after();
+          issue_pv(stage, j);
+          if (j + 1 < T) {
+            mbar_wait(&bar_kv_full[nstage], nphase);
+            tc_fence_after();
+            issue_s_half(nstage, 0);   // S halves were released before bar_p was completed
+            issue_s_half(nstage, 1);
+          }
         }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
@@ -216,11 +248,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     for (int j = 0; j < T; ++j) {
       const bool self = j < Ts;
       const int kv_valid = self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT);
-      mbar_wait(bar_s, j & 1);
-      if (j > 0) mbar_wait(bar_pv, (j - 1) & 1);   // previous P V done: P smem and the O accumulator are ours again
+      mbar_wait(&bar_s[0], j & 1);
       tc_fence_after();
+      bool pv_pending = j > 0;   // P smem and the O accumulator are ours again only once the previous P V has completed;
+                                 // that wait is deferred to the first point that needs it (first P store / a rescale)
       uint32_t raw[2][32];
       if (j == 0) {
+        mbar_wait(&bar_s[1], 0);
+        tc_fence_after();
         // first tile: one extra sweep over S to seed the row max (later tiles only check for growth, chunk by chunk)
         float mx0 = -INFINITY, mx1 = -INFINITY;
         tmem_ld32(tmem_s + lane_off, raw[0]);
@@ -240,6 +275,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
       for (int c = 0; c < KT / 32; ++c) {
         tmem_ld_wait();
+        if (c & 1) {   // both chunks of S half (c >> 1) are in registers: hand the half back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&bar_sfree[c >> 1]);
+        }
+        if (c == 1 && j > 0) {   // (on the first tile both halves were already awaited for the max sweep)
+          mbar_wait(&bar_s[1], j & 1);
+          tc_fence_after();
+        }
         if (c + 1 < KT / 32) tmem_ld32(tmem_s + lane_off + (c + 1) * 32, raw[(c + 1) & 1]);
         const bool full = (c + 1) * 32 <= kv_valid;
         if (j > 0) {
@@ -259,6 +302,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
           const bool grow = cm > m_used + kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
             const float m_new = grow ? cm : m_used;
+            if (pv_pending) { mbar_wait(bar_pv, (j - 1) & 1); tc_fence_after(); pv_pending = false; }
             rescale(grow ? fast_exp2(m_used - m_new) : 1.0f, c);
             m_used = m_new;
           }
@@ -277,6 +321,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             pk[i] = pack_h2(p0, p1);
           }
         }
+        if (pv_pending) { mbar_wait(bar_pv, (j - 1) & 1); tc_fence_after(); pv_pending = false; }
         uint8_t* chunk = prow + (c >> 1) * (QT * 128);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -322,6 +367,290 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant with EIGHT softmax warps (two threads per query row, one per 64-key half of the tile).  ncu on the 4-warp
+// kernel showed the XU (ex2) pipe only ~50 % busy and ~0.3 IPC per scheduler: with one softmax warp per scheduler and
+// CTA there is too little to overlap the fixed-latency chains (FFMA -> MUFU -> F2FP -> STS).  Here each scheduler holds
+// two softmax warps per CTA (four with two CTAs per SM); the two threads of a row agree on the row max through shared
+// memory and a 256-thread named barrier once per key tile.
+constexpr int ATT8_THREADS = 320;
+
+template <int D>
+__global__ void __launch_bounds__(ATT8_THREADS, ACfg<D>::kMinBlocks)
+attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+             const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
+             const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
+  using C = ACfg<D>;
+  constexpr int DP = C::kDpad, DV = C::kDv;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + C::kQBytes;
+  uint8_t* sKV = sP + C::kPBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::kStages * C::kStageBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_p = bars + 1;
+  uint64_t* bar_pv = bars + 2;
+  uint64_t* bar_s = bars + 3;        // [2]
+  uint64_t* bar_sfree = bars + 5;    // [2]
+  uint64_t* bar_kv_full = bars + 7;
+  uint64_t* bar_kv_empty = bars + 7 + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * C::kStages);
+  float* smax = reinterpret_cast<float*>(bars + 16);   // [2 (tile parity)][2 (half)][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
+  const int Ts = (a.L + KT - 1) / KT;
+  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
+  const int bidx = n / a.F;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_pv, 1);
+    for (int hh = 0; hh < 2; ++hh) {
+      mbar_init(&bar_s[hh], 1);
+      mbar_init(&bar_sfree[hh], 128);
+    }
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&bar_kv_full[s], 1);
+      mbar_init(&bar_kv_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, C::kQBytes);
+#pragma unroll
+      for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sQ + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * C::kStageBytes;
+        uint8_t* sV = sK + C::kKBytes;
+        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
+        const bool self = j < Ts;
+        const CUtensorMap* mk = self ? &map_k : &map_kb;
+        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
+        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;
+        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;
+#pragma unroll
+        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
+        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
+      constexpr uint32_t idesc_sh = umma_idesc_f16(QT, KT / 2);
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      auto issue_s_half = [&](int stage, int hh) {
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes) + hh * (KT / 2) * 128;
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
+          umma_f16_ss(tmem_s + hh * (KT / 2), ad, bd, idesc_sh, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_s[hh]);
+      };
+      auto issue_pv = [&](int stage, int j) {
+        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
+          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
+          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_pv);
+        umma_commit(&bar_kv_empty[stage]);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv_full[0], 0);
+      tc_fence_after();
+      issue_s_half(0, 0);
+      issue_s_half(0, 1);
+      for (int j = 0; j < T; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == C::kStages) { nstage = 0; nphase ^= 1; }
+        if constexpr (C::kStages >= 2) {
+          if (j + 1 < T) {
+            mbar_wait(&bar_kv_full[nstage], nphase);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              mbar_wait(&bar_sfree[hh], j & 1);
+              tc_fence_after();
+              issue_s_half(nstage, hh);
+            }
+          }
+          mbar_wait(bar_p, j & 1);
+          tc_fence_after();
+          issue_pv(stage, j);
+        } else {
+          mbar_wait(bar_p, j & 1);
+          tc_fence_after();
+          issue_pv(stage, j);
+          if (j + 1 < T) {
+            mbar_wait(&bar_kv_full[nstage], nphase);
+            tc_fence_after();
+            issue_s_half(nstage, 0);
+            issue_s_half(nstage, 1);
+          }
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: two threads per query row
+    const int qd = warp & 3;
+    const int hf = (warp - 2) >> 2;               // which 64-key half of every tile this thread owns
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t my_s = tmem_s + lane_off + hf * 64;
+    float m_used = -INFINITY;
+    uint8_t* prow = sP + hf * (QT * 128) + r * 128;   // P chunk hf, row r
+    const int sw = r & 7;
+    const float sc = a.scale_log2;
+
+    for (int j = 0; j < T; ++j) {
+      const bool self = j < Ts;
+      const int kv_valid = (self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT)) - hf * 64;   // valid keys in my half (may be <= 0)
+      mbar_wait(&bar_s[hf], j & 1);
+      tc_fence_after();
+      // pass 1: my half's row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(my_s + c * 32, raw);
+        tmem_ld_wait();
+        if ((c + 1) * 32 <= kv_valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(raw[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
+        }
+      }
+      float* sm = smax + (j & 1) * 256;
+      sm[hf * 128 + r] = fmaxf(mx0, mx1) * sc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float rowmax = fmaxf(sm[r], sm[128 + r]);
+      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
+      const float m_new = grow ? rowmax : m_used;
+      if (j > 0) {
+        mbar_wait(bar_pv, (j - 1) & 1);   // previous P V done: P smem and O are ours again
+        tc_fence_after();
+        if (hf == 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < DV / 16; ++c) {
+            uint32_t t16[16];
+            tmem_ld16(tmem_o + lane_off + c * 16, t16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
+            tmem_st16(tmem_o + lane_off + c * 16, t16);
+          }
+          tmem_st_wait();
+        }
+      }
+      m_used = m_new;
+      // pass 2: p = 2^(s*scale - m) -> fp16 -> my 64-key chunk of P
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(my_s + c * 32, raw);
+        tmem_ld_wait();
+        if (c == 1) {   // all my reads of this S half are done
+          tc_fence_before();
+          mbar_arrive(&bar_sfree[hf]);
+        }
+        uint32_t pk[16];
+        if ((c + 1) * 32 <= kv_valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = c * 32 + 2 * i;
+            const float p0 = c0 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)) : 0.f;
+            const float p1 = c0 + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)) : 0.f;
+            pk[i] = pack_h2(p0, p1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(prow + (((c * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // epilogue: O / denominator; the two threads of a row write alternate 8-column groups
+    mbar_wait(bar_pv, (T - 1) & 1);
+    tc_fence_after();
+    float o[DV];
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t raw16[16];
+      tmem_ld16(tmem_o + lane_off + c * 16, raw16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw16[i]);
+    }
+    tc_fence_before();
+    if (q0 + r < a.L) {
+      const float inv = 1.f / o[D];
+      __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        if ((c & 1) == hf) {
+          uint4 u;
+          u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+          u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+          u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+          u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
 template <int D>
 cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   using C = ACfg<D>;
@@ -339,8 +668,17 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
       return cudaErrorInvalidValue;
   }
   static bool attr = false;
+  static bool use8 = true;
   if (!attr) {
+    const char* ev = getenv("HV_ATTN_WARPS");
+    use8 = !(ev && ev[0] == '4');
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_kernel8<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_kernel8<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -356,7 +694,8 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   ka.vbt_stride = static_cast<int>(a.vbt_stride);
   ka.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   dim3 grid((a.L + QT - 1) / QT, a.heads, a.NF);
-  attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+  if (use8) attn_kernel8<D><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+  else attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
   return cudaGetLastError();
 }
 

@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t pack2h(__half a, __half b) {
 
 // QKV: [B*F*HW][3*C] rows (b, f, p); q at column h*D, k at C + h*D, v at 2C + h*D.
 template <int D>
-__global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B,
+__global__ void __launch_bounds__(256, (D <= 40) ? 2 : 1) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B,
                                                            int F, int HW, int heads, float scale_log2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -84,6 +84,32 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
     }
   }
 
+  // ---- prefetch V (issued before the softmax so the loads overlap it): the B fragment of P V needs
+  // (V[2t][c], V[2t+1][c]) with c = nt*8 + g, i.e. two rows of one column.  Each lane instead loads one half2
+  // (row 2t + (g&1), columns c&~1, c|1) and swaps halves with its partner lane g^1 (lane ^ 4): 4-byte loads, half as many.
+  constexpr int NTV = D / 8;
+  constexpr bool kPrefetchV = D <= 40;
+  uint32_t vfr[kPrefetchV ? NTV : 1][2][2];
+  auto load_v = [&](int nt, int kk, int hi) -> uint32_t {
+    const int j = kk * 16 + hi * 8 + 2 * t + (g & 1);
+    const int c = nt * 8 + (g & ~1);
+    return j < F ? ldg_h2(vb + j * fstride + c) : 0u;
+  };
+  auto fix_v = [&](uint32_t x) -> uint32_t {
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, 4);
+    // even g: (x.lo, y.lo)   odd g: (y.hi, x.hi)
+    return (g & 1) ? __byte_perm(y, x, 0x7632) : __byte_perm(x, y, 0x5410);
+  };
+  if constexpr (kPrefetchV) {
+#pragma unroll
+    for (int nt = 0; nt < NTV; ++nt)
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        vfr[nt][kk][0] = load_v(nt, kk, 0);
+        vfr[nt][kk][1] = load_v(nt, kk, 1);
+      }
+  }
+
   // ---- softmax over keys (columns); rows g / g+8 of each m-tile; quad (t) shares a row
   uint32_t pa[2][2][4];  // P as A fragments: [m-tile][k16 step over keys][4]
   float inv_sum[2][2];
@@ -126,19 +152,20 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
   // ---- O = P V, one n8 tile of the head dim at a time
   __half* ob = out + (static_cast<long long>(b) * F * HW + p) * C + h * D;
   const long long ostride = static_cast<long long>(HW) * C;
-  const __half zero = __float2half(0.f);
-#pragma unroll 1
-  for (int nt = 0; nt < D / 8; ++nt) {
-    const int c = nt * 8 + g;
+#pragma unroll
+  for (int nt = 0; nt < NTV; ++nt) {
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const int j = kk * 16 + 2 * t;
-      const __half v00 = j < F ? __ldg(vb + j * fstride + c) : zero;
-      const __half v01 = j + 1 < F ? __ldg(vb + (j + 1) * fstride + c) : zero;
-      const __half v10 = j + 8 < F ? __ldg(vb + (j + 8) * fstride + c) : zero;
-      const __half v11 = j + 9 < F ? __ldg(vb + (j + 9) * fstride + c) : zero;
-      const uint32_t b0 = pack2h(v00, v01), b1 = pack2h(v10, v11);
+      uint32_t x0, x1;
+      if constexpr (kPrefetchV) {
+        x0 = vfr[nt][kk][0];
+        x1 = vfr[nt][kk][1];
+      } else {
+        x0 = load_v(nt, kk, 0);
+        x1 = load_v(nt, kk, 1);
+      }
+      const uint32_t b0 = fix_v(x0), b1 = fix_v(x1);
       mma16816(o[0], pa[0][kk], b0, b1);
       mma16816(o[1], pa[1][kk], b0, b1);
     }

@@ -7,7 +7,7 @@
 //                               (BLOCK_N rows x 64 k) into a ring of 128B-swizzled shared-memory stages
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), accumulators
 //                               double-buffered in TMEM (2 x BLOCK_N columns); owns TMEM alloc/dealloc
-//   warps 2..9  epilogue      : tcgen05.ld of the accumulator (one output row per thread, two warps per TMEM lane
+//   warps 2..17 epilogue      : tcgen05.ld of the accumulator (one output row per thread, four warps per TMEM lane
 //                               quadrant splitting the columns), bias / time-embedding row vector / activation /
 //                               GEGLU / residual, fp16 store
 // The A operand is addressed through TMA only, so a 3x3 convolution over a channels-last (N,H,W,C) tensor is the
@@ -23,17 +23,27 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
+constexpr int kStagePerWarp = 128;  // per epilogue warp: its <= 64 bias values (LDS broadcast instead of an LDG per use)
+constexpr int GEMM_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
-template <int BLOCK_N>
+// MT = number of 128-row UMMA sub-tiles per CTA tile.  MT = 2 (256 x BLOCK_N tile, both accumulators fed by the same B
+// stage) halves the L2 -> shared-memory traffic per FLOP, which is what bounds the 128-row kernel (~58 B/clk/SM of TMA
+// fill sustains only ~60 % of the tensor pipe at 48 KB per 128x256x64 k-block); it is used when K is large enough that
+// the then single-buffered accumulator's epilogue is a small fraction of the tile (3x3 convs, wide linears).
+template <int BLOCK_N, int MT>
 struct Cfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;  // 48 KB (N=256), 36 KB (N=160), 32 KB (N=128) per stage
+  static constexpr int kATileBytes = MT * A_TILE_BYTES;
   static constexpr int kBTileBytes = BLOCK_N * BLOCK_K * 2;
-  static constexpr int kStageBytes = A_TILE_BYTES + kBTileBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N <= 256 ? 256 : 512;  // two accumulator stages, power-of-two allocation
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kAccStages = (2 * MT * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr int kAccCols = MT * BLOCK_N;                         // TMEM columns per accumulator stage
+  static constexpr int kTmemCols = kAccStages * kAccCols <= 256 ? 256 : 512;
+  static constexpr int kFixed = 16 * kStagePerWarp + 256 + 1024;         // epilogue staging + barriers + alignment slack
+  static constexpr int kStagesFit = (227 * 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 16 * kStagePerWarp + 1024;
 };
 
 struct TileCoord {
@@ -41,10 +51,10 @@ struct TileCoord {
   int n0, y0, x0;  // conv: first frame / output row / output col of the box
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const GemmProblem& p, int m_blk) {
+__device__ __forceinline__ TileCoord tile_coord(const GemmProblem& p, int m_blk, int rows_per_tile) {
   TileCoord t;
   if (p.a_mode == A_LINEAR) {
-    t.m0 = m_blk * BLOCK_M;
+    t.m0 = m_blk * rows_per_tile;
     t.n0 = t.y0 = t.x0 = 0;
   } else {
     int xb = m_blk % p.tiles_x;
@@ -67,6 +77,16 @@ __device__ __forceinline__ void store8(__half* dst, const float* v) {
   u.w = pack_h2(v[6], v[7]);
   *reinterpret_cast<uint4*>(dst) = u;
 }
+__device__ __forceinline__ void lds8(const __half* src, float* v) {  // shared memory, 16-byte aligned
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void load8(const __half* src, float* v) {
   uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -78,11 +98,12 @@ __device__ __forceinline__ void load8(const __half* src, float* v) {
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b, const GemmProblem p, const GemmEpilogue e) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, MT>;
+  constexpr int TILE_M = MT * BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -94,7 +115,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + BLOCK_M - 1) / BLOCK_M : p.tiles_n * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + TILE_M - 1) / TILE_M : p.tiles_n * p.tiles_y * p.tiles_x;
   const int n_per_batch = p.b_batch ? (p.b_rows + BLOCK_N - 1) / BLOCK_N : 0;
   const int n_tiles = p.b_batch ? p.b_batch * n_per_batch : (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = m_tiles * n_tiles;
@@ -107,8 +128,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
-      mbar_init(&bar_tempty[s], 8);
-    }
+      mbar_init(&bar_tempty[s], 16);
+    }  // (only stage 0 is used when the accumulator is single-buffered)
     fence_mbar_init();
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
@@ -127,11 +148,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const TileCoord tc = tile_coord(p, m_blk);
+        const TileCoord tc = tile_coord(p, m_blk, TILE_M);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + A_TILE_BYTES;
+          uint8_t* sb = sa + C::kATileBytes;
           mbar_arrive_expect_tx(&bar_full[stage], C::kStageBytes);
           if (p.a_mode == A_LINEAR) {
             if (p.k_split == 0 || kb < p.k_split)
@@ -168,172 +189,185 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + A_TILE_BYTES);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + C::kATileBytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = umma_desc_k_sw128(sa + mt * A_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_f16_ss(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&bar_empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps, 1 output row / thread)
-    // Two warps share each TMEM lane quadrant and split the tile's columns.  TMEM loads are double-buffered against
-    // the math of the previous chunk and the residual row is prefetched one chunk ahead (before the accumulator is
-    // even ready for chunk 0), so neither the TMEM nor the global-load latency sits on the critical path.
-    const int q = warp & 3;            // TMEM lane quadrant this warp may read
-    const int hsel = (warp - 2) >> 2;  // which half of the tile's columns
+    // ------------------------------------------------------------------ epilogue (16 warps, 1 output row / thread)
+    // The tensor pipe retires a 128x256x64 k-block in 512 clocks; for the K = 320..1280 linears of this network the
+    // epilogue (fp16 rounding chain, GEGLU, residual) needs more issue slots per tile than the mainloop needs clocks, so
+    // it is spread over 16 warps: four per TMEM lane quadrant, each owning a quarter of the tile's columns, in 16-column
+    // chunks with the TMEM load of the next chunk and the residual of the next chunk in flight behind the math.
+    const int q = warp & 3;             // TMEM lane quadrant this warp may read
+    const int cs = (warp - 2) >> 2;     // column slice of the tile handled by this warp (0..3)
     const int r = q * 32 + lane;
+    __half* sbias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + (warp - 2) * kStagePerWarp);
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int HALF = BLOCK_N / 2;
+    constexpr int SL = BLOCK_N / 4;     // columns per warp slice: 64 / 40 / 32
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const TileCoord tc = tile_coord(p, m_blk);
-      long long row;
-      bool row_ok;
-      if (p.a_mode == A_LINEAR) {
-        row = tc.m0 + r;
-        row_ok = row < p.M;
-      } else {
-        const int ix = r % p.bw, t2 = r / p.bw;
-        const int iy = t2 % p.bh, in = t2 / p.bh;
-        const int n = tc.n0 + in, y = tc.y0 + iy, x = tc.x0 + ix;
-        row_ok = n < p.NF && y < p.H && x < p.W;
-        row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      const TileCoord tc = tile_coord(p, m_blk, TILE_M);
+      // this warp's slice of the bias vector -> its private shared-memory strip (issued before the wait on the accumulator)
+      if (e.bias != nullptr) {
+        int bcol;
+        bool act;
+        if (!e.geglu) { bcol = n_blk * BLOCK_N + cs * SL + lane * 8; act = lane * 8 < SL; }
+        else { bcol = n_blk * BLOCK_N + cs * (BLOCK_N / 8) + (lane & 3) * 8 + (lane >> 2) * (BLOCK_N / 2); act = lane < 8; }  // 0-3 hidden, 4-7 gate
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (act && p.b_batch == 0 && bcol < p.N) bv = __ldg(reinterpret_cast<const uint4*>(e.bias + bcol));
+        __syncwarp();
+        if (act) *reinterpret_cast<uint4*>(sbias + lane * 8) = bv;
+        __syncwarp();
       }
-      const __half* __restrict__ rv = (e.rowvec != nullptr && row_ok) ? e.rowvec + (row / e.rows_per_group) * e.rowvec_ld : nullptr;
-      const __half* __restrict__ res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
-      const __half* __restrict__ bias = e.bias;
-      const float rowbias = (e.rowbias != nullptr && row_ok) ? __half2float(e.rowbias[row]) : 0.f;
-      __half* __restrict__ out = e.out + row * e.ldc;
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int rt = mt * BLOCK_M + r;   // row inside the CTA tile
+        long long row;
+        bool row_ok;
+        if (p.a_mode == A_LINEAR) {
+          row = tc.m0 + rt;
+          row_ok = row < p.M;
+        } else {
+          const int ix = rt % p.bw, t2 = rt / p.bw;
+          const int iy = t2 % p.bh, in = t2 / p.bh;
+          const int n = tc.n0 + in, y = tc.y0 + iy, x = tc.x0 + ix;
+          row_ok = n < p.NF && y < p.H && x < p.W;
+          row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+        }
+        const __half* __restrict__ rv = (e.rowvec != nullptr && row_ok) ? e.rowvec + (row / e.rows_per_group) * e.rowvec_ld : nullptr;
+        const __half* __restrict__ res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
+        const bool has_bias = e.bias != nullptr;
+        const float rowbias = (e.rowbias != nullptr && row_ok) ? __half2float(e.rowbias[row]) : 0.f;
+        __half* __restrict__ out = e.out + row * e.ldc;
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols + mt * BLOCK_N;
 
-      if (!e.geglu) {
-        constexpr int CW = (HALF % 32 == 0) ? 32 : 16;
-        constexpr int NC = HALF / CW;
-        const int tile_col0 = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + (n_blk % n_per_batch) * BLOCK_N : n_blk * BLOCK_N;
-        const int col_lim = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + ((p.b_rows + 7) & ~7) : e.n_valid;
-        const int colbase = tile_col0 + hsel * HALF;
-        uint32_t raw[2][CW];
-        uint4 rres[2][CW / 8];
-        auto fetch_res = [&](int c, int buf) {
+        if (!e.geglu) {
+          constexpr int NC = (SL + 15) / 16;     // 16-column chunks (the last one is 8 wide when SL = 40)
+          const int tile_col0 = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + (n_blk % n_per_batch) * BLOCK_N : n_blk * BLOCK_N;
+          const int col_lim = p.b_batch ? (n_blk / n_per_batch) * p.b_out_stride + ((p.b_rows + 7) & ~7) : e.n_valid;
+          const int colbase = tile_col0 + cs * SL;
+          uint32_t raw[2][16];
+          uint4 rres[2][2];
+          auto fetch = [&](int c, int buf) {
+            if (c * 16 + 16 <= SL) tmem_ld16(t_acc + cs * SL + c * 16, raw[buf]);
+            else tmem_ld8(t_acc + cs * SL + c * 16, raw[buf]);
 #pragma unroll
-          for (int g = 0; g < CW / 8; ++g) {
-            const int col = colbase + c * CW + g * 8;
-            rres[buf][g] = (res != nullptr && col < col_lim) ? __ldg(reinterpret_cast<const uint4*>(res + col)) : make_uint4(0, 0, 0, 0);
-          }
-        };
-        auto fetch_acc = [&](int c, int buf) {
-          if constexpr (CW == 32) tmem_ld32(t_acc + hsel * HALF + c * CW, raw[buf]);
-          else tmem_ld16(t_acc + hsel * HALF + c * CW, raw[buf]);
-        };
-        fetch_res(0, 0);
-        mbar_wait(&bar_tfull[acc], acc_phase);
-        tc_fence_after();
-        fetch_acc(0, 0);
+            for (int g = 0; g < 2; ++g) {
+              const int col = colbase + c * 16 + g * 8;
+              rres[buf][g] = (res != nullptr && c * 16 + g * 8 < SL && col < col_lim) ? __ldg(reinterpret_cast<const uint4*>(res + col)) : make_uint4(0, 0, 0, 0);
+            }
+          };
+          fetch(0, 0);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < NC) {
-            fetch_acc(c + 1, (c + 1) & 1);
-            fetch_res(c + 1, (c + 1) & 1);
-          }
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) fetch(c + 1, (c + 1) & 1);
 #pragma unroll
-          for (int g = 0; g < CW / 8; ++g) {
-            const int col = colbase + c * CW + g * 8;
-            if (col < col_lim) {
-              float v[8], t[8];
+            for (int g = 0; g < 2; ++g) {
+              const int col = colbase + c * 16 + g * 8;
+              if (c * 16 + g * 8 < SL && col < col_lim) {
+                float v[8], t[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
-              if (bias != nullptr) {
-                load8(bias + col, t);
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
+                if (has_bias) {
+                  lds8(sbias + c * 16 + g * 8, t);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += t[i];
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
-              if (rv != nullptr) {
-                load8(rv + col, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
-              }
-              if (e.act == ACT_RELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-              } else if (e.act == ACT_SILU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
-              }
-              if (res != nullptr) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&rres[c & 1][g]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __half22float2(h2[i]);
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
+                  for (int i = 0; i < 8; ++i) v[i] += t[i];
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
+                if (rv != nullptr) {
+                  load8(rv + col, t);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+                }
+                if (e.act == ACT_RELU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (e.act == ACT_SILU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
+                }
+                if (res != nullptr) {
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&rres[c & 1][g]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    v[2 * i] += f.x;
+                    v[2 * i + 1] += f.y;
+                  }
+                }
+                if (row_ok) store8(out + col, v);
               }
-              if (row_ok) store8(out + col, v);
+            }
+          }
+        } else {
+          // GEGLU (BLOCK_N == 256): tile columns [0,128) are "hidden", [128,256) the matching "gate" rows of the packed
+          // weight; this warp owns hidden columns [cs*32, cs*32+32) and their gates.  The fp16 roundings of the reference's
+          // eager path (proj output, gelu output, product) are reproduced with packed-half arithmetic.
+          constexpr int NC = (BLOCK_N / 8) / 16;
+          const int hcol0 = cs * (BLOCK_N / 8);
+          uint32_t hraw[2][16], graw[2][16];
+          auto fetch = [&](int c, int buf) {
+            tmem_ld16(t_acc + hcol0 + c * 16, hraw[buf]);
+            tmem_ld16(t_acc + BLOCK_N / 2 + hcol0 + c * 16, graw[buf]);
+          };
+          fetch(0, 0);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) fetch(c + 1, (c + 1) & 1);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int ocol = n_blk * (BLOCK_N / 2) + hcol0 + c * 16 + g * 8;
+              float bh[8], bg[8];
+              if (has_bias) {
+                lds8(sbias + c * 16 + g * 8, bh);
+                lds8(sbias + 32 + c * 16 + g * 8, bg);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 h2 = __floats2half2_rn(__uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i],
+                                                     __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1]);
+                const float2 gf = __half22float2(__floats2half2_rn(__uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i],
+                                                                   __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1]));
+                const __half2 ge = __floats2half2_rn(gelu_erf_fast(gf.x), gelu_erf_fast(gf.y));
+                const __half2 pr = __hmul2(h2, ge);
+                o[i] = *reinterpret_cast<const uint32_t*>(&pr);
+              }
+              if (row_ok && ocol < e.n_valid) *reinterpret_cast<uint4*>(out + ocol) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
-      } else {
-        // GEGLU (BLOCK_N == 256): tile columns [0,128) are "hidden", [128,256) the matching "gate" rows of the packed
-        // weight; this warp-half owns hidden columns [hsel*64, hsel*64+64) and their gates.
-        constexpr int CW = 16, NC = (BLOCK_N / 4) / CW;
-        const int hcol0 = hsel * (BLOCK_N / 4);
-        uint32_t hraw[2][CW], graw[2][CW];
-        auto fetch_acc = [&](int c, int buf) {
-          tmem_ld16(t_acc + hcol0 + c * CW, hraw[buf]);
-          tmem_ld16(t_acc + BLOCK_N / 2 + hcol0 + c * CW, graw[buf]);
-        };
-        mbar_wait(&bar_tfull[acc], acc_phase);
-        tc_fence_after();
-        fetch_acc(0, 0);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < NC) fetch_acc(c + 1, (c + 1) & 1);
-#pragma unroll
-          for (int g = 0; g < CW / 8; ++g) {
-            const int pcol = n_blk * BLOCK_N + hcol0 + c * CW + g * 8;                // packed column of the hidden part
-            const int ocol = n_blk * (BLOCK_N / 2) + hcol0 + c * CW + g * 8;          // output column
-            if (ocol < e.n_valid) {
-              float hv[8], gv[8], t[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                hv[i] = __uint_as_float(hraw[c & 1][g * 8 + i]);
-                gv[i] = __uint_as_float(graw[c & 1][g * 8 + i]);
-              }
-              if (bias != nullptr) {
-                load8(bias + pcol, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hv[i] += t[i];
-                load8(bias + pcol + BLOCK_N / 2, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) gv[i] += t[i];
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) hv[i] = r16(hv[i]) * r16(gelu_erf_f(r16(gv[i])));
-              if (row_ok) store8(out + ocol, hv);
-            }
-          }
-        }
-      }
+      }  // sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -347,12 +381,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
 }  // namespace
 
-void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw) {
+void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw, int rows) {
   long long best = -1;
-  int b_n = 1, b_h = 1, b_w = 128;
-  for (int w = 128; w >= 1; w >>= 1) {
-    for (int h = 128 / w; h >= 1; h >>= 1) {
-      int n = 128 / (w * h);
+  int b_n = 1, b_h = 1, b_w = rows;
+  for (int w = rows; w >= 1; w >>= 1) {
+    for (int h = rows / w; h >= 1; h >>= 1) {
+      int n = rows / (w * h);
       auto up = [](int a, int b) { return static_cast<long long>((a + b - 1) / b) * b; };
       long long padded = up(NF, n) * up(H, h) * up(W, w);
       if (best < 0 || padded < best) {  // ties keep the widest box along W (longest contiguous TMA rows)
@@ -368,44 +402,39 @@ void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw) {
   *bw = b_w;
 }
 
+template <int BN, int MT>
+static cudaError_t launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p, const GemmEpilogue& e,
+                            int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  gemm_kernel<BN, MT><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
-                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream) {
-  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + BLOCK_M - 1) / BLOCK_M : p.tiles_n * p.tiles_y * p.tiles_x;
+                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub) {
+  const int tile_m = BLOCK_M * m_sub;
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + tile_m - 1) / tile_m : p.tiles_n * p.tiles_y * p.tiles_x;
   const int n_tiles = p.b_batch ? p.b_batch * ((p.b_rows + block_n - 1) / block_n) : (p.N + block_n - 1) / block_n;
   const int tiles = m_tiles * n_tiles;
   if (tiles <= 0 || p.num_k_blocks <= 0) return cudaErrorInvalidValue;
   if (p.b_batch && (e.bias || e.rowvec || e.residual || e.geglu || (p.b_out_stride % 8))) return cudaErrorInvalidValue;
   if (e.geglu && block_n != 256) return cudaErrorInvalidValue;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  cudaError_t err;
-  if (block_n == 256) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      err = cudaFuncSetAttribute(gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes);
-      if (err != cudaSuccess) return err;
-      attr_set = true;
-    }
-    gemm_kernel<256><<<grid, GEMM_THREADS, Cfg<256>::kSmemBytes, stream>>>(a0, a1, b, p, e);
-  } else if (block_n == 160) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      err = cudaFuncSetAttribute(gemm_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<160>::kSmemBytes);
-      if (err != cudaSuccess) return err;
-      attr_set = true;
-    }
-    gemm_kernel<160><<<grid, GEMM_THREADS, Cfg<160>::kSmemBytes, stream>>>(a0, a1, b, p, e);
-  } else if (block_n == 128) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      err = cudaFuncSetAttribute(gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes);
-      if (err != cudaSuccess) return err;
-      attr_set = true;
-    }
-    gemm_kernel<128><<<grid, GEMM_THREADS, Cfg<128>::kSmemBytes, stream>>>(a0, a1, b, p, e);
-  } else {
-    return cudaErrorInvalidValue;
+  if (m_sub == 1) {
+    if (block_n == 256) return launch_t<256, 1>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 160) return launch_t<160, 1>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 128) return launch_t<128, 1>(a0, a1, b, p, e, grid, stream);
+  } else if (m_sub == 2) {
+    if (block_n == 256) return launch_t<256, 2>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 160) return launch_t<160, 2>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 128) return launch_t<128, 2>(a0, a1, b, p, e, grid, stream);
   }
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace hv

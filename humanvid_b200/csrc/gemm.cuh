@@ -34,7 +34,7 @@ struct GemmProblem {
   int cin_blocks = 0;              // conv: 64-channel blocks per tap
   int cin = 0;                     // conv s2: channels of the source (parity offset in the folded 2C axis)
   int H = 0, W = 0, NF = 0;        // conv: OUTPUT height / width / frame count
-  int bn = 1, bh = 1, bw = 128;    // conv: tile box (bn*bh*bw == 128)
+  int bn = 1, bh = 1, bw = 128;    // conv: tile box (bn*bh*bw == 128 or 256 rows per CTA tile)
   int tiles_n = 0, tiles_y = 0, tiles_x = 0;
   // batched B operand (V^T = Wv * X^T per frame): B is a 3-D map (K, b_rows, b_batch); output columns of batch n
   // start at n * b_out_stride (a multiple of 8) so every frame's token segment is 16-byte aligned for TMA readers.
@@ -45,9 +45,10 @@ struct GemmProblem {
 // a0/a1: TMA maps of the A operand (see make_* helpers in tma.h), b: TMA map of the packed weights [N][K].
 // block_n must be 128, 160 or 256 (256 required for geglu); 160 = two exact tiles for the 320-wide layers.
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
-                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream);
+                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub = 1);
 
 // Picks the (bn, bh, bw) output-tile box with the least padding for an NF x H x W output.
-void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw);
+// (rows = 128 or 256 output pixels per CTA tile; every box dimension is a power of two <= 256)
+void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw, int rows = 128);
 
 }  // namespace hv

@@ -20,7 +20,7 @@ inline unsigned blocks_for(long long n, int num_sms) {
 
 // (B, C, F, H, W) [fp16 or fp32] -> (B*F, H, W, C) fp16.  Tiled transpose of the (C, HW) plane of each (b, f).
 template <typename T>
-__global__ void ncfhw_to_nhwc_kernel(const T* __restrict__ x, __half* __restrict__ out, int B, int C, int F, int HW) {
+__global__ void ncfhw_to_nhwc_kernel(const T* __restrict__ x, __half* __restrict__ out, int B, int C, int F, int HW, int ldo) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;  // b*F + f
   const int b = n / F, f = n % F;
@@ -32,7 +32,7 @@ __global__ void ncfhw_to_nhwc_kernel(const T* __restrict__ x, __half* __restrict
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    if (c < C && p < HW) out[(static_cast<long long>(n) * HW + p) * C + c] = __float2half_rn(tile[threadIdx.x][i]);
+    if (c < C && p < HW) out[(static_cast<long long>(n) * HW + p) * ldo + c] = __float2half_rn(tile[threadIdx.x][i]);
   }
 }
 
@@ -226,13 +226,14 @@ __global__ void dbg_gemm_kernel(const __half* __restrict__ a, long long lda, con
 
 #define HV_LAUNCH_CHECK() return cudaGetLastError()
 
-cudaError_t launch_ncfhw_to_nhwc(const void* x, __half* out, int B, int C, int F, int H, int W, int src_fp32, cudaStream_t s) {
+cudaError_t launch_ncfhw_to_nhwc(const void* x, __half* out, int B, int C, int F, int H, int W, int src_fp32, cudaStream_t s, int ldo) {
+  if (ldo <= 0) ldo = C;
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B * F), block(32, 8);
   if (src_fp32)
-    ncfhw_to_nhwc_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), out, B, C, F, HW);
+    ncfhw_to_nhwc_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), out, B, C, F, HW, ldo);
   else
-    ncfhw_to_nhwc_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), out, B, C, F, HW);
+    ncfhw_to_nhwc_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), out, B, C, F, HW, ldo);
   HV_LAUNCH_CHECK();
 }
 cudaError_t launch_nhwc_to_ncfhw(const __half* x, int ldx, __half* out, int B, int C, int F, int H, int W, cudaStream_t s) {

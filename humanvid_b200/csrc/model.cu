@@ -171,7 +171,7 @@ struct hv_model {
   // optional per-category device timing (bench.py's roofline): events bracket every operator launch
   enum Cat { CAT_GEMM = 0, CAT_CONV = 1, CAT_ATTN = 2, CAT_TATTN = 3, CAT_NORM = 4, CAT_MISC = 5, CAT_N = 6 };
   bool profiling = false;
-  struct Rec { int cat; cudaEvent_t a, b; double flops; };
+  struct Rec { int cat; cudaEvent_t a, b; double flops; long long m, n, k; const char* label; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
@@ -184,17 +184,18 @@ struct hv_model {
     return ev_pool[ev_used++];
   }
   struct Timed {  // RAII bracket around one operator
-    hv_model* m; int cat; double flops; cudaEvent_t a{};
-    Timed(hv_model* mm, int c, double f) : m(mm), cat(c), flops(f) {
+    hv_model* m; int cat; double flops; long long M, N, K; const char* label; cudaEvent_t a{};
+    Timed(hv_model* mm, int c, double f, const char* lb = "", long long M_ = 0, long long N_ = 0, long long K_ = 0)
+        : m(mm), cat(c), flops(f), M(M_), N(N_), K(K_), label(lb) {
       if (m->profiling && !m->ar.dry) { a = m->ev(); cudaEventRecord(a, m->st); }
     }
     ~Timed() {
-      if (m->profiling && !m->ar.dry) { cudaEvent_t b = m->ev(); cudaEventRecord(b, m->st); m->recs.push_back({cat, a, b, flops}); }
+      if (m->profiling && !m->ar.dry) { cudaEvent_t b = m->ev(); cudaEventRecord(b, m->st); m->recs.push_back({cat, a, b, flops, M, N, K, label}); }
     }
   };
 
   // ---- UNet
-  ConvDirect conv_in;
+  Conv3 conv_in;  // 4 input channels zero-padded to 64: runs on the implicit-GEMM kernel
   Lin te1, te2;
   struct DownBlk { std::vector<ResnetW> res; std::vector<SpatialW> attn; std::vector<MotionW> mm; bool has_down = false; Conv3 down; };
   struct UpBlk { std::vector<ResnetW> res; std::vector<SpatialW> attn; std::vector<MotionW> mm; bool has_up = false; Conv3 up; };
@@ -386,7 +387,7 @@ struct hv_model {
     const int* ch = cfg.block_out_channels;
     const int temb = ch[0] * 4;
     const bool mm = cfg.use_motion_module != 0;
-    conv_in = conv_direct("conv_in", ch[0], cfg.in_channels);
+    conv_in = conv3("conv_in", ch[0], cfg.in_channels);
     te1 = lin("time_embedding.linear_1", temb, ch[0]);
     te2 = lin("time_embedding.linear_2", temb, temb);
     int prev = ch[0];
@@ -488,7 +489,7 @@ struct hv_model {
     float* stats = static_cast<float*>(ar.alloc(sizeof(float) * groupnorm_scratch_floats(x.C + C2, x.NF, x.H * x.W, cfg.norm_groups, sms)));
     if (ar.dry) return out;
     launches += 3;
-    Timed tm(this, CAT_NORM, 0);
+    Timed tm(this, CAT_NORM, 0, "groupnorm", x.rows(), x.C + C2, 0);
     ck(launch_groupnorm(x.p, x.C, x2 ? x2->p : nullptr, C2, n.g, n.b, out.p, x.NF, x.H * x.W, cfg.norm_groups, n.eps, silu ? 1 : 0, stats, sms, st),
        "groupnorm");
     return out;
@@ -499,7 +500,7 @@ struct hv_model {
     if (pre_add && x_new) *x_new = alloc_act(x.NF, x.H, x.W, x.C);
     if (ar.dry) return out;
     launches += 1;
-    Timed tm(this, CAT_NORM, 0);
+    Timed tm(this, CAT_NORM, 0, "layernorm", x.rows(), x.C, 0);
     ck(launch_layernorm(x.p, n.g, n.b, out.p, x.rows(), x.C, n.eps, pre_add, rows_per_b, (pre_add && x_new) ? x_new->p : nullptr, pe, x.H * x.W, F, st),
        "layernorm");
     return out;
@@ -508,7 +509,7 @@ struct hv_model {
             const hv_epilogue* ep) {
     if (ar.dry) return;
     launches += 1;
-    Timed tm(this, CAT_GEMM, 2.0 * M * w.rows * w.cols);
+    Timed tm(this, CAT_GEMM, 2.0 * M * w.rows * w.cols, (ep && ep->geglu) ? "gemm_geglu" : ((ep && ep->residual) ? "gemm_res" : "gemm"), M, w.rows, w.cols);
     ckop(op_gemm(A, lda, A2, lda2, K1, w.p, out, ldc, M, w.rows, w.cols, ep, st), "gemm");
   }
   // y = x W^T + b (+ residual)
@@ -537,7 +538,7 @@ struct hv_model {
     ep.act = act;
     if (residual) { ep.residual = residual->p; ep.ldr = residual->C; }
     launches += 1;
-    Timed tm(this, CAT_CONV, 2.0 * out.rows() * c.cout * 9.0 * c.cin);
+    Timed tm(this, CAT_CONV, 2.0 * out.rows() * c.cout * 9.0 * c.cin, stride == 1 ? "conv3" : "conv3_s2", out.rows(), c.cout_pad, 9LL * c.cin_pad);
     ckop(op_conv3x3(x.p, c.w.p, out.p, c.cout_pad, x.NF, x.H, x.W, c.cin_pad, c.cout_pad, stride, &ep, st), "conv3x3");
     return out;
   }
@@ -580,7 +581,7 @@ struct hv_model {
       ep.residual = res.p;
       ep.ldr = res.C;
       launches += 1;
-      Timed tm(this, CAT_CONV, 2.0 * x.rows() * r.cout * 9.0 * r.cout);
+      Timed tm(this, CAT_CONV, 2.0 * x.rows() * r.cout * 9.0 * r.cout, "conv3_res", x.rows(), r.cout, 9LL * r.c2.cin_pad);
       ckop(op_conv3x3(h2.p, r.c2.w.p, out.p, r.cout, x.NF, x.H, x.W, r.c2.cin_pad, r.c2.cout_pad, 1, &ep, st), "resnet conv2");
     }
     return out;
@@ -608,7 +609,7 @@ struct hv_model {
       // V^T[C][frame n: n*Lp + j] = Wv [C][C] * n1^T : weights are the "A" operand, activations the batched "B" operand
       if (!ar.dry) {
         launches += 1;
-        Timed tm(this, CAT_GEMM, 2.0 * tokens * C * C);
+        Timed tm(this, CAT_GEMM, 2.0 * tokens * C * C, "gemm_vt", vrows, tokens, C);
         ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, vrows, x.NF, L, Lp, C, w.vones, st), "V^T gemm");
       }
       const bool use_bank = w.bank != nullptr;
@@ -639,7 +640,7 @@ struct hv_model {
         a.vt_stride = Lp; a.vbt_stride = Lbp;
         launches += 1;
         const double nb_frames = x.NF - a.nf_nobank;
-        Timed tm(this, CAT_ATTN, 4.0 * L * w.C * (static_cast<double>(x.NF) * L + nb_frames * a.Lb));
+        Timed tm(this, CAT_ATTN, 4.0 * L * w.C * (static_cast<double>(x.NF) * L + nb_frames * a.Lb), "attn", x.NF, L, w.d);
         cudaError_t e = launch_attention(a, sms, st);
         if (e != cudaSuccess) fail(HV_ERR_CUDA, "attention (%s): %s %s", w.name.c_str(), cudaGetErrorString(e), tma_last_error());
       }
@@ -678,7 +679,7 @@ struct hv_model {
     Tens o = alloc_act(t.NF, t.H, t.W, C);
     if (!ar.dry) {
       launches += 1;
-      Timed tm(this, CAT_TATTN, 4.0 * t.rows() * F * C);
+      Timed tm(this, CAT_TATTN, 4.0 * t.rows() * F * C, "tattn", t.rows(), F, C);
       ck(launch_temporal_attention(qkv, o.p, B, F, t.H * t.W, heads, d, st), "temporal attention");
     }
     hv_epilogue ep{};
@@ -735,17 +736,16 @@ struct hv_model {
     if (!ar.dry) { launches += 1; ck(launch_timestep_embedding(timestep, tsin, B, ch[0], st), "timestep embedding"); }
     __half* e1 = op_small_linear(tsin, te1, B, HV_ACT_NONE);
     __half* emb = op_small_linear(e1, te2, B, HV_ACT_SILU);
-    // conv_in (+ pose_cond_fea)
-    Tens x0 = alloc_act(NF, H, W, cfg.in_channels);
+    // conv_in (+ pose_cond_fea as the epilogue residual); the 4 latent channels are zero-padded to one 64-wide k-block
+    Tens x0 = alloc_act(NF, H, W, conv_in.cin_pad);
     Tens pc = pose ? alloc_act(NF, H, W, ch[0]) : Tens{};
-    Tens h = alloc_act(NF, H, W, ch[0]);
     if (!ar.dry) {
       launches += 2 + (pose ? 1 : 0);
-      ck(launch_ncfhw_to_nhwc(sample, x0.p, B, cfg.in_channels, F, H, W, 0, st), "sample layout");
+      ck(cudaMemsetAsync(x0.p, 0, static_cast<size_t>(x0.numel()) * 2, st), "memset");
+      ck(launch_ncfhw_to_nhwc(sample, x0.p, B, cfg.in_channels, F, H, W, 0, st, x0.C), "sample layout");
       if (pose) ck(launch_ncfhw_to_nhwc(pose, pc.p, B, ch[0], F, H, W, 0, st), "pose layout");
-      ck(launch_conv3x3_direct(x0.p, conv_in.w, conv_in.bias, h.p, NF, H, W, conv_in.cin, conv_in.cout, 1, HV_ACT_NONE, pose ? pc.p : nullptr, sms, st),
-         "conv_in");
     }
+    Tens h = op_conv3(x0, conv_in, 1, nullptr, 1, HV_ACT_NONE, pose ? &pc : nullptr);
     std::vector<Tens> skips{h};
     for (size_t i = 0; i < down.size(); ++i) {
       auto& d = down[i];
@@ -887,6 +887,23 @@ int hv_set_profiling(hv_handle h, int32_t enable) {
   if (!h) return HV_ERR_INVALID;
   h->profiling = enable != 0;
   return HV_OK;
+}
+
+int hv_dump_profile(hv_handle h, const char* path) {
+  if (!h || !path) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    FILE* f = fopen(path, "w");
+    if (!f) fail(HV_ERR_INVALID, "cannot open %s", path);
+    if (!h->recs.empty()) ck(cudaEventSynchronize(h->recs.back().b), "profile sync");
+    fprintf(f, "idx,cat,label,M,N,K,ms,tflops\n");
+    int i = 0;
+    for (const auto& r : h->recs) {
+      float t = 0;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      fprintf(f, "%d,%d,%s,%lld,%lld,%lld,%.4f,%.1f\n", i++, r.cat, r.label, r.m, r.n, r.k, t, t > 0 ? r.flops / 1e9 / t : 0.0);
+    }
+    fclose(f);
+  });
 }
 
 int hv_get_profile(hv_handle h, double* ms, double* flops, int64_t* count, int32_t ncat) {

@@ -45,8 +45,25 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
     int ldc, cc;
     if (c0 < C1) { src = x1; ldc = C1; cc = c0; } else { src = x2; ldc = C2; cc = c0 - C1; }
     const int row_end = min(HW, (blockIdx.x + 1) * rows_per_block);
-    for (int r = blockIdx.x * rows_per_block + rl; r < row_end; r += rpi) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<long long>(n) * HW + r) * ldc + cc));
+    const __half* base = src + static_cast<long long>(n) * HW * ldc + cc;
+    int r = blockIdx.x * rows_per_block + rl;
+    for (; r + 3 * rpi < row_end; r += 4 * rpi) {  // four independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r + k * rpi) * ldc));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s[i] += f[2 * i] + f[2 * i + 1];
+          q[i] += f[2 * i] * f[2 * i] + f[2 * i + 1] * f[2 * i + 1];
+        }
+      }
+    }
+    for (; r < row_end; r += rpi) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * ldc));
       float f[8];
       unpack8(u, f);
 #pragma unroll
@@ -96,99 +113,144 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
+// grid (slabs, NF), thread = (row lane, 8-channel vector) like the statistics kernel: the thread's channels are fixed, so
+// gamma/beta/mean/rstd fold into one per-channel scale and shift kept in registers, and the row loop has no integer
+// division and one FFMA + SiLU per element.
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
-                                long long total_vecs, int HW, int groups, float eps, int silu, const float* __restrict__ stats) {
+                                int HW, int groups, int rows_per_block, int silu, const float* __restrict__ stats) {
   const int C = C1 + C2, vecs = C / 8, cpg = C / groups;
-  (void)eps;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / vecs;
-    const int c0 = static_cast<int>(i % vecs) * 8;
-    const int n = static_cast<int>(row / HW);
-    const __half* src = c0 < C1 ? x1 + row * C1 + c0 : x2 + row * C2 + (c0 - C1);
-    float f[8], gm[8], bt[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+  const int n = blockIdx.y;
+  const int rl = threadIdx.x / vecs, v = threadIdx.x % vecs, rpi = blockDim.x / vecs;
+  const int c0 = v * 8;
+  float sc[8], sh[8];
+  {
+    float gm[8], bt[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c0)), gm);
     unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c0)), bt);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g = (c0 + 2 * k) / cpg;
-      const float mean = stats[(static_cast<long long>(n) * groups + g) * 2], rstd = stats[(static_cast<long long>(n) * groups + g) * 2 + 1];
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2));
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        float y = r16((f[2 * k + j] - mean) * rstd * gm[2 * k + j] + bt[2 * k + j]);
-        if (silu) y = silu_f(y);
-        f[2 * k + j] = y;
+        sc[2 * k + j] = st.y * gm[2 * k + j];
+        sh[2 * k + j] = fmaf(-st.x, sc[2 * k + j], bt[2 * k + j]);
       }
     }
-    *reinterpret_cast<uint4*>(out + row * C + c0) = pack8(f);
   }
+  const __half* src;
+  int ldc;
+  if (c0 < C1) { src = x1 + static_cast<long long>(n) * HW * C1 + c0; ldc = C1; } else { src = x2 + static_cast<long long>(n) * HW * C2 + (c0 - C1); ldc = C2; }
+  __half* dst = out + static_cast<long long>(n) * HW * C + c0;
+  const int row_end = min(HW, (blockIdx.x + 1) * rows_per_block);
+  auto emit = [&](const uint4& u, int r) {
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = r16(fmaf(f[j], sc[j], sh[j]));
+      if (silu) y = __fdividef(y, 1.0f + __expf(-y));
+      f[j] = y;
+    }
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * C) = pack8(f);
+  };
+  int r = blockIdx.x * rows_per_block + rl;
+  for (; r + 3 * rpi < row_end; r += 4 * rpi) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(r + k * rpi) * ldc));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(u[k], r + k * rpi);
+  }
+  for (; r < row_end; r += rpi) emit(__ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * ldc)), r);
 }
 
 // ---------------------------------------------------------------- LayerNorm: one warp per row
 template <int MAXV>  // vectors (8 halves) per lane
-__global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                  __half* __restrict__ out, long long rows, int C, float eps, const __half* __restrict__ pre_add,
                                  long long rows_per_group, __half* __restrict__ x_out, const __half* __restrict__ pe, int hw, int F) {
   const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int vecs = C / 8;
-  float v[MAXV][8];
-  float sum = 0.f;
-  const __half* add = pre_add ? pre_add + (row / rows_per_group) * C : nullptr;
+  uint4 nxt[MAXV];
+  float gmr[MAXV][8], btr[MAXV][8];   // this lane's gamma / beta (its channel vectors are the same for every row)
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int vi = lane + 32 * k;
     if (vi < vecs) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + vi * 8)), v[k]);
-      if (add) {
-        float a[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(add + vi * 8)), a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j] + a[j]);
-        if (x_out) *reinterpret_cast<uint4*>(x_out + row * C + vi * 8) = pack8(v[k]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[k][j];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)), gmr[k]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + vi * 8)), btr[k]);
     }
   }
+  auto fetch = [&](long long r) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < vecs) nxt[k] = __ldg(reinterpret_cast<const uint4*>(x + r * C + vi * 8));
+    }
+  };
+  if (row < rows) fetch(row);
+  for (; row < rows; row += warps_total) {
+    float v[MAXV][8];
+    float sum = 0.f;
+    const __half* add = pre_add ? pre_add + (row / rows_per_group) * C : nullptr;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < vecs) {
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < vecs) unpack8(nxt[k], v[k]);
+    }
+    if (row + warps_total < rows) fetch(row + warps_total);  // next row's loads fly while this row is reduced
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[k][j] - mean;
-        sq += d * d;
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < vecs) {
+        if (add) {
+          float a[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(add + vi * 8)), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j] + a[j]);
+          if (x_out) *reinterpret_cast<uint4*>(x_out + row * C + vi * 8) = pack8(v[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[k][j];
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
-  const __half* pe_row = pe ? pe + static_cast<long long>((row / hw) % F) * C : nullptr;
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < vecs) {
-      float gm[8], bt[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)), gm);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + vi * 8)), bt);
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < vecs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * gm[j] + bt[j];
-      if (pe_row) {
-        float pv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(pe_row + vi * 8)), pv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j]) + pv[j];
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[k][j] - mean;
+          sq += d * d;
+        }
       }
-      *reinterpret_cast<uint4*>(out + row * C + vi * 8) = pack8(v[k]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+    const __half* pe_row = pe ? pe + static_cast<long long>((row / hw) % F) * C : nullptr;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * gmr[k][j] + btr[k][j];
+        if (pe_row) {
+          float pv[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(pe_row + vi * 8)), pv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j]) + pv[j];
+        }
+        *reinterpret_cast<uint4*>(out + row * C + vi * 8) = pack8(v[k]);
+      }
     }
   }
 }
@@ -228,10 +290,7 @@ cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2,
   gn_stats_kernel<<<dim3(slabs, NF), threads, threads * 8 * sizeof(float), stream>>>(x1, C1, x2, C2, HW, groups, rows_per_block, partial);
   const int total_g = NF * groups;
   gn_finalize_kernel<<<(total_g + 127) / 128, 128, 0, stream>>>(partial, stats, total_g, groups, slabs, 1.f / (static_cast<float>(HW) * (C / groups)), eps);
-  const long long total = static_cast<long long>(NF) * HW * vecs;
-  long long blocks = (total + 255) / 256;
-  if (blocks > num_sms * 16LL) blocks = num_sms * 16LL;
-  gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x1, C1, x2, C2, gamma, beta, out, total, HW, groups, eps, silu, stats);
+  gn_apply_kernel<<<dim3(slabs, NF), threads, 0, stream>>>(x1, C1, x2, C2, gamma, beta, out, HW, groups, rows_per_block, silu, stats);
   return cudaGetLastError();
 }
 
@@ -241,7 +300,9 @@ cudaError_t launch_layernorm(const __half* x, const __half* gamma, const __half*
   if (C % 8) return cudaErrorInvalidValue;
   const int vecs = C / 8;
   const int wpb = 8;
-  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  long long blocks = (rows + wpb - 1) / wpb;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;  // persistent: 8 blocks x 8 warps per SM, each warp streams rows with prefetch
+  const unsigned grid = static_cast<unsigned>(blocks);
   if (rows_per_group <= 0) rows_per_group = 1;
   if (hw <= 0) hw = 1;
   if (F <= 0) F = 1;

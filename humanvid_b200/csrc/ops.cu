@@ -74,6 +74,14 @@ static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
   return best;
 }
 
+// 256-row CTA tiles (two UMMA sub-tiles sharing one B stage) when K is large enough to amortise the then
+// single-buffered accumulator's epilogue and there is enough work to fill the machine.
+static int pick_m_sub(int64_t rows, int64_t N, int bn, int64_t K, int sms) {
+  if (K < 2816) return 1;  // 3x3 convs (K >= 2880) and the widest linears only: below that the exposed epilogue costs more than the L2 traffic saved
+  const int64_t tiles2 = ((rows + 255) / 256) * ((N + bn - 1) / bn);
+  return tiles2 >= sms ? 2 : 1;
+}
+
 int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_t K1, const __half* W, __half* out, int64_t ldc,
             int64_t M, int64_t N, int64_t K, const hv_epilogue* ep, cudaStream_t stream) {
   const int sms = device_sms();
@@ -95,11 +103,12 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   }
   CUtensorMap ma0, ma1, mb;
   const int64_t Ka = split ? K1 : K;
-  if (!make_map_2d(&ma0, A, M, Ka, lda, 128)) { set_error("hv_op_gemm A map: %s", tma_last_error()); return HV_ERR_TMA; }
-  ma1 = ma0;
-  if (split && !make_map_2d(&ma1, A2, M, K - K1, lda2, 128)) { set_error("hv_op_gemm A2 map: %s", tma_last_error()); return HV_ERR_TMA; }
   const int64_t m_tiles = (M + 127) / 128;
   const int bn = pick_block_n(N, m_tiles, geglu, sms);
+  const int m_sub = pick_m_sub(M, N, bn, K, sms);
+  if (!make_map_2d(&ma0, A, M, Ka, lda, 128 * m_sub)) { set_error("hv_op_gemm A map: %s", tma_last_error()); return HV_ERR_TMA; }
+  ma1 = ma0;
+  if (split && !make_map_2d(&ma1, A2, M, K - K1, lda2, 128 * m_sub)) { set_error("hv_op_gemm A2 map: %s", tma_last_error()); return HV_ERR_TMA; }
   if (!make_map_2d(&mb, W, N, K, K, bn)) { set_error("hv_op_gemm W map: %s", tma_last_error()); return HV_ERR_TMA; }
   GemmProblem p;
   p.M = static_cast<int>(M);
@@ -109,7 +118,7 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   p.k_split = split ? static_cast<int>(K1 / 64) : 0;
   GemmEpilogue e;
   fill_epilogue(e, ep, out, ldc, N);
-  cudaError_t err = launch_gemm(ma0, ma1, mb, p, e, bn, sms, stream);
+  cudaError_t err = launch_gemm(ma0, ma1, mb, p, e, bn, sms, stream, m_sub);
   if (err != cudaSuccess) return cuda_fail(err, "hv_op_gemm launch");
   return HV_OK;
 }
@@ -165,7 +174,9 @@ int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int6
   p.H = static_cast<int>(Ho);
   p.W = static_cast<int>(Wo);
   p.NF = static_cast<int>(NF);
-  choose_conv_box(p.NF, p.H, p.W, &p.bn, &p.bh, &p.bw);
+  const int bn_guess = pick_block_n(Cout, (static_cast<int64_t>(NF) * Ho * Wo + 127) / 128, false, sms);
+  const int m_sub = pick_m_sub(static_cast<int64_t>(NF) * Ho * Wo, Cout, bn_guess, 9 * Cin, sms);
+  choose_conv_box(p.NF, p.H, p.W, &p.bn, &p.bh, &p.bw, 128 * m_sub);
   p.tiles_n = (p.NF + p.bn - 1) / p.bn;
   p.tiles_y = (p.H + p.bh - 1) / p.bh;
   p.tiles_x = (p.W + p.bw - 1) / p.bw;
@@ -173,12 +184,11 @@ int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int6
   CUtensorMap ma, mb;
   bool ok = stride == 1 ? make_map_nhwc(&ma, X, NF, H, W, Cin, p.bn, p.bh, p.bw) : make_map_nhwc_s2(&ma, X, NF, H, W, Cin, p.bn, p.bh, p.bw);
   if (!ok) { set_error("hv_op_conv3x3 X map: %s", tma_last_error()); return HV_ERR_TMA; }
-  const int64_t m_tiles = static_cast<int64_t>(p.tiles_n) * p.tiles_y * p.tiles_x;
-  const int bn = pick_block_n(Cout, m_tiles, false, sms);
+  const int bn = bn_guess;
   if (!make_map_2d(&mb, Wp, Cout, 9 * Cin, 9 * Cin, bn)) { set_error("hv_op_conv3x3 W map: %s", tma_last_error()); return HV_ERR_TMA; }
   GemmEpilogue e;
   fill_epilogue(e, ep, out, ldc, Cout);
-  cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream);
+  cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream, m_sub);
   if (err != cudaSuccess) return cuda_fail(err, "hv_op_conv3x3 launch");
   return HV_OK;
 }

@@ -100,6 +100,8 @@ int64_t hv_last_launch_count(hv_handle h);
  * returns summed milliseconds, algorithmic FLOPs (2*MAC, unpadded shapes) and launch counts of the LAST forward. */
 int hv_set_profiling(hv_handle h, int32_t enable);
 int hv_get_profile(hv_handle h, double* ms, double* flops, int64_t* count, int32_t ncat);
+/* One CSV line per timed launch of the last profiled forward: idx,cat,label,M,N,K,ms,tflops. */
+int hv_dump_profile(hv_handle h, const char* path);
 
 #ifdef __cplusplus
 }

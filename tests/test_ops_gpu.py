@@ -32,7 +32,7 @@ def gemm(A, W, M, N, K, ep=None, A2=None, K1=0, ldc=None):
     return out
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1000, 320, 320), (6912, 640, 1280), (333, 2560, 320), (4096, 384, 320)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1000, 320, 320), (6912, 640, 1280), (333, 2560, 320), (4096, 384, 320), (40000, 640, 1280), (38000, 320, 2560), (41000, 1280, 1024)])
 def test_gemm_plain(M, N, K):
     A, W = dev(M, K, seed=1), dev(N, K, scale=K ** -0.5, seed=2)
     out = gemm(A, W, M, N, K)
@@ -97,7 +97,8 @@ def conv_ref(x_nhwc, w, bias, stride):
 
 @pytest.mark.parametrize("NF,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 128, 1), (3, 24, 18, 128, 320, 1), (4, 12, 9, 320, 64, 1),
                                                       (2, 96, 72, 64, 64, 1), (2, 16, 16, 64, 128, 2), (3, 24, 18, 128, 128, 2),
-                                                      (2, 96, 72, 64, 64, 2), (5, 8, 8, 640, 8, 1)])
+                                                      (2, 96, 72, 64, 64, 2), (5, 8, 8, 640, 8, 1), (8, 96, 72, 128, 320, 1), (24, 48, 36, 192, 640, 1), (48, 24, 18, 128, 1280, 1),
+                                                      (16, 96, 72, 128, 320, 2)])
 def test_conv3x3(NF, H, W, Cin, Cout, stride):
     x = dev(NF, H, W, Cin, seed=20)
     w = dev(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21)
