@@ -651,6 +651,285 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant with SIXTEEN softmax warps, one CTA per SM: four threads per query row, each owning 32 keys of a tile, so the
+// thread keeps its scores in registers (one TMEM read per tile) and hands the S buffer back to the MMA warp at once.
+// S and P are double-buffered (TMEM 2 x 128 columns + O; shared memory 2 x 32 KB), K/V tiles go through a 3-4 stage ring:
+// the tensor pipe works one key tile ahead and the softmax warps only ever wait for each other (row-max exchange).
+constexpr int ATT16_THREADS = 576;
+
+template <int D>
+struct A16Cfg {
+  using B = ACfg<D>;
+  static constexpr int kPBuf = 2 * QT * 128;                          // one P buffer (two 64-key chunks)
+  static constexpr int kFixed = B::kQBytes + 2 * kPBuf + 256 + 4096 + 1024;
+  static constexpr int kFit = (227 * 1024 - kFixed) / B::kStageBytes;
+  static constexpr int kStages = kFit > 4 ? 4 : (kFit < 1 ? 1 : kFit);
+  static constexpr int kSmemBytes = kFixed + kStages * B::kStageBytes;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT16_THREADS, 1)
+attn_kernel16(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+              const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
+              const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
+  using C = ACfg<D>;
+  using C16 = A16Cfg<D>;
+  constexpr int DP = C::kDpad, DV = C::kDv, NST = C16::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + C::kQBytes;                   // [2] buffers
+  uint8_t* sKV = sP + 2 * C16::kPBuf;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * C::kStageBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_s = bars + 1;        // [2] S buffer b holds a fresh tile
+  uint64_t* bar_sfree = bars + 3;    // [2] all 512 softmax threads have read S buffer b
+  uint64_t* bar_p = bars + 5;        // [2] P buffer b written (512 arrivals)
+  uint64_t* bar_pv = bars + 7;       // [2] the P V of a tile with parity b has completed
+  uint64_t* bar_kv_full = bars + 9;
+  uint64_t* bar_kv_empty = bars + 9 + NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * NST);
+  float* smax = reinterpret_cast<float*>(bars + 32);   // [2 (tile parity)][4 (key quarter)][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
+  const int Ts = (a.L + KT - 1) / KT;
+  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
+  const int bidx = n / a.F;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_s[b], 1);
+      mbar_init(&bar_sfree[b], 512);
+      mbar_init(&bar_p[b], 512);
+      mbar_init(&bar_pv[b], 1);
+    }
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&bar_kv_full[s], 1);
+      mbar_init(&bar_kv_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;   // S buffers at columns 0 and 128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, C::kQBytes);
+#pragma unroll
+      for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sQ + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + stage * C::kStageBytes;
+        uint8_t* sV = sK + C::kKBytes;
+        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
+        const bool self = j < Ts;
+        const CUtensorMap* mk = self ? &map_k : &map_kb;
+        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
+        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;
+        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;
+#pragma unroll
+        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
+        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
+        if (++stage == NST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_s = [&](int stage, int b) {
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
+          umma_f16_ss(tmem_base + b * 128, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_s[b]);
+      };
+      auto issue_pv = [&](int stage, int j) {
+        const uint32_t aP = smem_u32(sP + (j & 1) * C16::kPBuf);
+        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
+          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
+          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_pv[j & 1]);
+        umma_commit(&bar_kv_empty[stage]);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      for (int j = 0; j < T; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == NST) { nstage = 0; nphase ^= 1; }
+        if constexpr (NST >= 2) {
+          if (j + 1 < T) {
+            const int b = (j + 1) & 1;
+            mbar_wait(&bar_kv_full[nstage], nphase);
+            mbar_wait(&bar_sfree[b], ((((j + 1) >> 1) & 1) ^ 1));   // previous tile on this S buffer (if any) has been read
+            tc_fence_after();
+            issue_s(nstage, b);
+          }
+          mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(stage, j);
+        } else {
+          mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(stage, j);
+          if (j + 1 < T) {
+            const int b = (j + 1) & 1;
+            mbar_wait(&bar_kv_full[nstage], nphase);
+            mbar_wait(&bar_sfree[b], ((((j + 1) >> 1) & 1) ^ 1));
+            tc_fence_after();
+            issue_s(nstage, b);
+          }
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: four threads per query row
+    const int qd = warp & 3;
+    const int cq = (warp - 2) >> 2;               // which 32-key quarter of every tile this thread owns
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    float m_used = -INFINITY;
+    const int sw = r & 7;
+    const float sc = a.scale_log2;
+
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      const bool self = j < Ts;
+      const int kv_valid = (self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT)) - cq * 32;   // valid keys in my quarter (may be <= 0)
+      mbar_wait(&bar_s[b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_off + b * 128 + cq * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_sfree[b]);                 // scores are in registers: the S buffer can be overwritten
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (kv_valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(raw[i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
+      }
+      float* sm = smax + b * 512;
+      sm[cq * 128 + r] = fmaxf(mx0, mx1) * sc;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float rowmax = fmaxf(fmaxf(sm[r], sm[128 + r]), fmaxf(sm[256 + r], sm[384 + r]));
+      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in the four threads of the row
+      const float m_new = grow ? rowmax : m_used;
+      if (j > 0 && cq == 0 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O holds tiles 0..j-1
+        tc_fence_after();
+        const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+          uint32_t t16[16];
+          tmem_ld16(tmem_o + lane_off + c * 16, t16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
+          tmem_st16(tmem_o + lane_off + c * 16, t16);
+        }
+        tmem_st_wait();
+      }
+      m_used = m_new;
+      uint32_t pk[16];
+      if (kv_valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = 2 * i < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)) : 0.f;
+          const float p1 = 2 * i + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)) : 0.f;
+          pk[i] = pack_h2(p0, p1);
+        }
+      }
+      if (j >= 2) {   // P buffer b was last read by the P V of tile j-2
+        mbar_wait(&bar_pv[b], ((j - 2) >> 1) & 1);
+      }
+      uint8_t* prow = sP + b * C16::kPBuf + (cq >> 1) * (QT * 128) + r * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(prow + ((((cq & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar_p[b]);
+    }
+    // epilogue: O / denominator; the four threads of a row write interleaved 8-column groups
+    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    float o[DV];
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t raw16[16];
+      tmem_ld16(tmem_o + lane_off + c * 16, raw16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw16[i]);
+    }
+    tc_fence_before();
+    if (q0 + r < a.L) {
+      const float inv = 1.f / o[D];
+      __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        if ((c & 3) == cq) {
+          uint4 u;
+          u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+          u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+          u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+          u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 template <int D>
 cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   using C = ACfg<D>;
@@ -668,10 +947,15 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
       return cudaErrorInvalidValue;
   }
   static bool attr = false;
-  static bool use8 = true;
+  static int nwarps = 8;
   if (!attr) {
     const char* ev = getenv("HV_ATTN_WARPS");
-    use8 = !(ev && ev[0] == '4');
+    if (ev) nwarps = atoi(ev);
+    if (nwarps != 4 && nwarps != 8 && nwarps != 16) nwarps = 8;
+    {
+      cudaError_t e16 = cudaFuncSetAttribute(attn_kernel16<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, A16Cfg<D>::kSmemBytes);
+      if (e16 != cudaSuccess) return e16;
+    }
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -694,7 +978,8 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   ka.vbt_stride = static_cast<int>(a.vbt_stride);
   ka.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   dim3 grid((a.L + QT - 1) / QT, a.heads, a.NF);
-  if (use8) attn_kernel8<D><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+  if (nwarps == 16) attn_kernel16<D><<<grid, ATT16_THREADS, A16Cfg<D>::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+  else if (nwarps == 8) attn_kernel8<D><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
   else attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
   return cudaGetLastError();
 }

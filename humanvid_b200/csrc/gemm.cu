@@ -237,6 +237,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         if (act) *reinterpret_cast<uint4*>(sbias + lane * 8) = bv;
         __syncwarp();
       }
+      if (e.residual != nullptr && !e.geglu) {
+        // pull this thread's residual row segments towards L2 while the tile's MMAs are still running
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int rt = mt * BLOCK_M + r;
+          long long prow;
+          bool pok;
+          if (p.a_mode == A_LINEAR) {
+            prow = tc.m0 + rt;
+            pok = prow < p.M;
+          } else {
+            const int ix = rt % p.bw, t2 = rt / p.bw;
+            const int iy = t2 % p.bh, in = t2 / p.bh;
+            const int n = tc.n0 + in, y = tc.y0 + iy, x = tc.x0 + ix;
+            pok = n < p.NF && y < p.H && x < p.W;
+            prow = (static_cast<long long>(n) * p.H + y) * p.W + x;
+          }
+          const int pcol = n_blk * BLOCK_N + cs * SL;
+          if (pok && pcol < e.n_valid) {
+            const __half* pa = e.residual + prow * e.ldr + pcol;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            if (SL * 2 > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 32));   // slices wider than 64 B may straddle another line
+          }
+        }
+      }
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1

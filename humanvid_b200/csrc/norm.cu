@@ -167,90 +167,82 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
 }
 
 // ---------------------------------------------------------------- LayerNorm: one warp per row
-template <int MAXV>  // vectors (8 halves) per lane
+// LPR lanes cooperate on one row (32/LPR rows per warp), each lane owning up to 5 vectors of 8 halves: C = 320 -> 8 lanes
+// x 5 vectors, 640 -> 16 x 5, 1280 -> 32 x 5, so every lane is busy and five 16-byte loads per lane are in flight.
+template <int LPR>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                  __half* __restrict__ out, long long rows, int C, float eps, const __half* __restrict__ pre_add,
                                  long long rows_per_group, __half* __restrict__ x_out, const __half* __restrict__ pe, int hw, int F) {
+  constexpr int MAXV = 5;
+  constexpr int RPW = 32 / LPR;   // rows per warp
   const int lane = threadIdx.x & 31;
-  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sub = lane % LPR, rsel = lane / LPR;
+  const long long warp_global = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row = warp_global * RPW + rsel;
+  const bool row_ok = row < rows;
   const int vecs = C / 8;
-  uint4 nxt[MAXV];
-  float gmr[MAXV][8], btr[MAXV][8];   // this lane's gamma / beta (its channel vectors are the same for every row)
+  float v[MAXV][8];
+  float sum = 0.f;
+  const __half* add = (pre_add && row_ok) ? pre_add + (row / rows_per_group) * C : nullptr;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int vi = lane + 32 * k;
-    if (vi < vecs) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)), gmr[k]);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + vi * 8)), btr[k]);
+    const int vi = sub + LPR * k;
+    if (row_ok && vi < vecs) unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + vi * 8)), v[k]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
     }
   }
-  auto fetch = [&](long long r) {
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < vecs) nxt[k] = __ldg(reinterpret_cast<const uint4*>(x + r * C + vi * 8));
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = sub + LPR * k;
+    if (row_ok && vi < vecs) {
+      if (add) {
+        float a[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(add + vi * 8)), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j] + a[j]);
+        if (x_out) *reinterpret_cast<uint4*>(x_out + row * C + vi * 8) = pack8(v[k]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[k][j];
     }
-  };
-  if (row < rows) fetch(row);
-  for (; row < rows; row += warps_total) {
-    float v[MAXV][8];
-    float sum = 0.f;
-    const __half* add = pre_add ? pre_add + (row / rows_per_group) * C : nullptr;
+  }
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < vecs) unpack8(nxt[k], v[k]);
-    }
-    if (row + warps_total < rows) fetch(row + warps_total);  // next row's loads fly while this row is reduced
+  for (int o = LPR / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < vecs) {
-        if (add) {
-          float a[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(add + vi * 8)), a);
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = sub + LPR * k;
+    if (vi < vecs) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j] + a[j]);
-          if (x_out) *reinterpret_cast<uint4*>(x_out + row * C + vi * 8) = pack8(v[k]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[k][j];
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        sq += d * d;
       }
     }
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / C;
-    float sq = 0.f;
+  for (int o = LPR / 2; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  const __half* pe_row = (pe && row_ok) ? pe + static_cast<long long>((row / hw) % F) * C : nullptr;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < vecs) {
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = sub + LPR * k;
+    if (row_ok && vi < vecs) {
+      float gm[8], bt[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + vi * 8)), gm);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + vi * 8)), bt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[k][j] - mean;
-          sq += d * d;
-        }
+      for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * gm[j] + bt[j];
+      if (pe_row) {
+        float pv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pe_row + vi * 8)), pv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j]) + pv[j];
       }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / C + eps);
-    const __half* pe_row = pe ? pe + static_cast<long long>((row / hw) % F) * C : nullptr;
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < vecs) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = (v[k][j] - mean) * rstd * gmr[k][j] + btr[k][j];
-        if (pe_row) {
-          float pv[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(pe_row + vi * 8)), pv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j]) + pv[j];
-        }
-        *reinterpret_cast<uint4*>(out + row * C + vi * 8) = pack8(v[k]);
-      }
+      *reinterpret_cast<uint4*>(out + row * C + vi * 8) = pack8(v[k]);
     }
   }
 }
@@ -299,23 +291,20 @@ cudaError_t launch_layernorm(const __half* x, const __half* gamma, const __half*
                              cudaStream_t stream) {
   if (C % 8) return cudaErrorInvalidValue;
   const int vecs = C / 8;
-  const int wpb = 8;
-  long long blocks = (rows + wpb - 1) / wpb;
-  if (blocks > 148LL * 8) blocks = 148LL * 8;  // persistent: 8 blocks x 8 warps per SM, each warp streams rows with prefetch
-  const unsigned grid = static_cast<unsigned>(blocks);
+  if (vecs > 160) return cudaErrorInvalidValue;
   if (rows_per_group <= 0) rows_per_group = 1;
   if (hw <= 0) hw = 1;
   if (F <= 0) F = 1;
-  if (vecs <= 32)
-    layernorm_kernel<1><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
-  else if (vecs <= 64)
-    layernorm_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
-  else if (vecs <= 96)
-    layernorm_kernel<3><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
-  else if (vecs <= 160)
-    layernorm_kernel<5><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
+  const int lpr = vecs <= 40 ? 8 : (vecs <= 80 ? 16 : 32);
+  const int wpb = 8;
+  const long long warps = (rows + (32 / lpr) - 1) / (32 / lpr);
+  const unsigned grid = static_cast<unsigned>((warps + wpb - 1) / wpb);
+  if (lpr == 8)
+    layernorm_kernel<8><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
+  else if (lpr == 16)
+    layernorm_kernel<16><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
   else
-    return cudaErrorInvalidValue;
+    layernorm_kernel<32><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, C, eps, pre_add, rows_per_group, x_out, pe, hw, F);
   return cudaGetLastError();
 }
 

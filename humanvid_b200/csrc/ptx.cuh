@@ -207,13 +207,16 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 // erf-GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the fp16 rounding that follows)
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * fast_exp2(-z * z * 1.4426950408889634f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float erfc_abs = poly * t * fast_exp2(-z * z * 1.4426950408889634f);   // 1 - erf(|x|/sqrt2)
+  const float hx = 0.5f * x;
+  // 0.5x(1 + sign(x) erf) = x - 0.5x*erfc for x >= 0, 0.5x*erfc for x < 0
+  return x >= 0.f ? fmaf(-hx, erfc_abs, x) : hx * erfc_abs;
 }
 
 }  // namespace hv
