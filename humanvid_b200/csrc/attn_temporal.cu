@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t pack2h(__half a, __half b) {
 
 // QKV: [B*F*HW][3*C] rows (b, f, p); q at column h*D, k at C + h*D, v at 2C + h*D.
 template <int D>
-__global__ void __launch_bounds__(256, (D <= 40) ? 2 : 1) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B,
+__global__ void __launch_bounds__(256, (D <= 40) ? 3 : 1) temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B,
                                                            int F, int HW, int heads, float scale_log2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;

@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 #include "kernels.h"
@@ -63,6 +64,10 @@ static void fill_epilogue(GemmEpilogue& e, const hv_epilogue* ep, __half* out, i
 // ties go to the wider tile (fewer A re-reads, better UMMA smem ratio) unless that leaves SMs idle.
 static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
   if (geglu) return 256;
+  if (const char* ev = getenv("HV_GEMM_BN")) {  // tuning/debug override
+    const int v = atoi(ev);
+    if (v == 128 || v == 160 || v == 256) return v;
+  }
   const int cand[3] = {256, 160, 128};
   int best = 128;
   int64_t best_pad = -1;
