@@ -12,8 +12,9 @@ A "step" is one per-timestep pass of the hot path for one clip: UNet3DConditionM
                  copied from pinned host memory and the prediction read back to the host every step.
   reference arm  (--impl reference) the reference-equivalent PyTorch path (the oracle; the reference itself cannot be
                  imported: diffusers is not installed) in fp32 on the host CPU cores, on a bounded sample of the same
-                 workload: 2 of the 48 frame-passes at full 96x72 latent resolution (all spatial work is per frame; the
-                 temporal attention over 2 instead of 24 frames is 0.2 % of the FLOPs), scaled linearly in frames.
+                 workload: 1 of the step's 48 frame-passes at full 96x72 latent resolution (all spatial work is per
+                 frame; the temporal attention, degenerate on one frame, is 0.2 % of the FLOPs), scaled linearly in
+                 frame-passes (~30 s per sample on 128 cores; the whole step would take ~25 min).
 """
 from __future__ import annotations
 
@@ -106,8 +107,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_reference_sample(steps, warmup, frames=2):
-    """Oracle (reference-equivalent PyTorch, fp32) on the host cores: UNet forward on `frames` frame-passes per CFG half."""
+def cpu_reference_sample(steps, warmup, frames=1, cfg_batch=1):
+    """Oracle (reference-equivalent PyTorch, fp32) on the host cores.  One sample = UNet forward over `frames` frames of
+    `cfg_batch` CFG halves at the full 96x72 latent: frames * cfg_batch of the step's 48 frame-passes (~30 s on 128 cores, the
+    whole 48 would take ~25 min).  frames/s counts a frame as the CFG pair of passes, like the native arm."""
     import torch
 
     from oracle import hv_oracle as O
@@ -117,9 +120,9 @@ def cpu_reference_sample(steps, warmup, frames=2):
     m = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval()
     synthetic_init_(m, 7, "cpu")
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(2, 4, frames, H, W, generator=g)
-    ehs = torch.randn(2, 1, XDIM, generator=g)
-    pose = torch.randn(2, CH[0], frames, H, W, generator=g) * 0.5
+    x = torch.randn(cfg_batch, 4, frames, H, W, generator=g)
+    ehs = torch.randn(cfg_batch, 1, XDIM, generator=g)
+    pose = torch.randn(cfg_batch, CH[0], frames, H, W, generator=g) * 0.5
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -129,15 +132,16 @@ def cpu_reference_sample(steps, warmup, frames=2):
             if i >= warmup:
                 times.append(dt)
     t = sum(times) / len(times)
-    return {"frames_per_s": frames / t, "s_per_sample": t, "cores": nthreads,
-            "sample": f"UNet forward on {frames} of 24 frames x CFG batch 2 at full 96x72 latent (={2 * frames} of 48 frame-passes), fp32, "
-                      f"{nthreads} threads; frames/s = {frames} / t"}
+    passes = frames * cfg_batch
+    return {"frames_per_s": 0.5 * passes / t, "s_per_sample": t, "cores": nthreads,
+            "sample": f"UNet forward on {passes} of the step's 48 frame-passes ({frames} frame(s) x {cfg_batch} CFG half) at the full 96x72 latent, "
+                      f"fp32, {nthreads} threads, {len(times)} timed sample(s) of {t:.1f} s; frames/s = ({passes} / 2) / t"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_reference_sample(max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
+    r = cpu_reference_sample(max(1, min(args.steps, 2)), min(args.warmup, 1))
     line = {"metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": r["frames_per_s"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 24 / r["frames_per_s"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -262,7 +266,7 @@ def run_native(args, rank, world, local_rank):
     gemm_n = int(cat_n[0] + cat_n[1])
     achieved = gemm_fl / 1e9 / gemm_ms if gemm_ms > 0 else 0.0
 
-    cpu = cpu_reference_sample(2, 1) if not args.no_cpu_baseline else None
+    cpu = cpu_reference_sample(1, 0) if not args.no_cpu_baseline else None
     value = world * F / (ms / 1000.0)
     line = {
         "metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

@@ -14,6 +14,8 @@
 // same kernel: k-block kb = (tap, 64-channel block) and the tile of 128 output pixels is a (bn x bh x bw) box whose
 // input window is fetched with the box shifted by the tap offset; TMA's out-of-bounds zero fill is the padding.
 // Stride-2 convolutions view the same memory as (N, H/2, 2, W/2, 2*C) so each tap is again a dense box.
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -25,6 +27,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
 constexpr int kStagePerWarp = 128;  // per epilogue warp: its <= 64 bias values (LDS broadcast instead of an LDG per use)
+constexpr int kMaxStages = 8;
+constexpr int kMaxSmem = 227 * 1024;
 constexpr int GEMM_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
 // MT = number of 128-row UMMA sub-tiles per CTA tile.  MT = 2 (256 x BLOCK_N tile, both accumulators fed by the same B
@@ -42,8 +46,10 @@ struct Cfg {
   static constexpr int kFixed = 16 * kStagePerWarp + 256 + 1024;         // epilogue staging + barriers + alignment slack
   static constexpr int kStagesFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kBarBytes = (2 * kMaxStages + 6) * 8 + 16;       // full[8] empty[8] tfull[2] tempty[2] bpanel[2] + TMEM slot
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 16 * kStagePerWarp + 1024;
+  // B-stationary mode: the CTA's whole BLOCK_N x K weight panel stays in shared memory, the ring holds A tiles only
+  static constexpr int kBstFixed = kBarBytes + 16 * kStagePerWarp + 1024;
 };
 
 struct TileCoord {
@@ -98,7 +104,11 @@ __device__ __forceinline__ void load8(const __half* src, float* v) {
   }
 }
 
-template <int BLOCK_N, int MT>
+// BST ("B-stationary"): every tile a CTA visits has the same n_blk (the host makes gridDim.x a multiple of n_tiles), so
+// the CTA loads its BLOCK_N x K weight panel into shared memory once and streams only A afterwards.  For the K <= 640
+// linears of the two high-resolution levels this removes the per-tile re-fetch of B from L2 (as many bytes as A at
+// BLOCK_N = 128..256), and L2 -> SM fill is what bounds those GEMMs.
+template <int BLOCK_N, int MT, bool BST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b, const GemmProblem p, const GemmEpilogue e) {
@@ -106,11 +116,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   constexpr int TILE_M = MT * BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* bar_empty = bar_full + C::kStages;
-  uint64_t* bar_tfull = bar_empty + C::kStages;
+  const int nstages = BST ? p.bst_stages : C::kStages;
+  constexpr int kRingStageBytes = BST ? C::kATileBytes : C::kStageBytes;
+  uint8_t* ring = smem + (BST ? p.num_k_blocks * C::kBTileBytes : 0);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + nstages * kRingStageBytes);
+  uint64_t* bar_empty = bar_full + kMaxStages;
+  uint64_t* bar_tfull = bar_empty + kMaxStages;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_bpanel = bar_tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_bpanel + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,10 +136,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int nkb = p.num_k_blocks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
+    mbar_init(bar_bpanel, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 16);
@@ -146,14 +161,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (BST && static_cast<int>(blockIdx.x) < num_tiles) {
+        mbar_arrive_expect_tx(bar_bpanel, nkb * C::kBTileBytes);
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(smem + kb * C::kBTileBytes, &map_b, bar_bpanel, kb * BLOCK_K, (blockIdx.x % n_tiles) * BLOCK_N);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const TileCoord tc = tile_coord(p, m_blk, TILE_M);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sa = ring + stage * kRingStageBytes;
           uint8_t* sb = sa + C::kATileBytes;
-          mbar_arrive_expect_tx(&bar_full[stage], C::kStageBytes);
+          mbar_arrive_expect_tx(&bar_full[stage], kRingStageBytes);
           if (p.a_mode == A_LINEAR) {
             if (p.k_split == 0 || kb < p.k_split)
               tma_load_2d(sa, &map_a0, &bar_full[stage], kb * BLOCK_K, tc.m0);
@@ -170,11 +190,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                           tc.y0 - (dy == 0 ? 1 : 0), tc.n0);
             }
           }
-          if (p.b_batch)
-            tma_load_3d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, (n_blk % n_per_batch) * BLOCK_N, n_blk / n_per_batch);
-          else
-            tma_load_2d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (!BST) {
+            if (p.b_batch)
+              tma_load_3d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, (n_blk % n_per_batch) * BLOCK_N, n_blk / n_per_batch);
+            else
+              tma_load_2d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -186,6 +208,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (BST && static_cast<int>(blockIdx.x) < num_tiles) mbar_wait(bar_bpanel, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -193,8 +216,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + C::kATileBytes);
+          const uint32_t sa = smem_u32(ring + stage * kRingStageBytes);
+          const uint64_t bdesc = umma_desc_k_sw128(BST ? smem_u32(smem + kb * C::kBTileBytes) : sa + C::kATileBytes);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t adesc = umma_desc_k_sw128(sa + mt * A_TILE_BYTES);
@@ -203,7 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               umma_f16_ss(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&bar_empty[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_tfull[acc]);
         if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -432,11 +455,33 @@ static cudaError_t launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const 
                             int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
-  gemm_kernel<BN, MT><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  gemm_kernel<BN, MT, false><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  return cudaGetLastError();
+}
+
+// B-stationary launch; returns cudaErrorNotSupported when the shape does not qualify (caller falls back to the ring).
+template <int BN>
+static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmProblem p, const GemmEpilogue& e,
+                              int m_tiles, int n_tiles, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN, 1>;
+  const int panel = p.num_k_blocks * C::kBTileBytes;
+  int stages = (kMaxSmem - C::kBstFixed - panel) / C::kATileBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int per_col = num_sms / n_tiles;  // CTAs sharing one n_blk
+  if (stages < 3 || per_col < 1 || m_tiles < 2 * per_col) return cudaErrorNotSupported;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  p.bst_stages = stages;
+  const int smem = panel + stages * C::kATileBytes + C::kBstFixed;
+  gemm_kernel<BN, 1, true><<<per_col * n_tiles, GEMM_THREADS, smem, stream>>>(a0, a1, b, p, e);
   return cudaGetLastError();
 }
 
@@ -450,6 +495,14 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   if (p.b_batch && (e.bias || e.rowvec || e.residual || e.geglu || (p.b_out_stride % 8))) return cudaErrorInvalidValue;
   if (e.geglu && block_n != 256) return cudaErrorInvalidValue;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  static const int bst_env = [] { const char* v = getenv("HV_GEMM_BST"); return v ? atoi(v) : 1; }();
+  if (bst_env && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && n_tiles <= num_sms) {
+    cudaError_t r = cudaErrorNotSupported;
+    if (block_n == 256) r = launch_bst<256>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (block_n == 160) r = launch_bst<160>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (block_n == 128) r = launch_bst<128>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (r != cudaErrorNotSupported) return r;
+  }
   if (m_sub == 1) {
     if (block_n == 256) return launch_t<256, 1>(a0, a1, b, p, e, grid, stream);
     if (block_n == 160) return launch_t<160, 1>(a0, a1, b, p, e, grid, stream);

@@ -20,15 +20,20 @@ def bench(M, N, K, bias=True, res=True, n_valid=0, iters=20, geglu=False):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
-M = 331776
-for (N, K) in [(320, 320), (960, 320), (320, 1280)]:
-    for bn in ("", "128", "160", "256"):
-        if bn: os.environ["HV_GEMM_BN"] = bn
-        else: os.environ.pop("HV_GEMM_BN", None)
-        t_full = bench(M, N, K)
-        t_nores = bench(M, N, K, res=False)
-        t_nobias = bench(M, N, K, bias=False, res=False)
-        t_nostore = bench(M, N, K, bias=False, res=False, n_valid=8)
-        print(f"N={N} K={K} BN={bn or 'auto'}: full {t_full:.3f}  no-res {t_nores:.3f}  no-bias/res {t_nobias:.3f}  no-store {t_nostore:.3f} ms", flush=True)
-os.environ.pop("HV_GEMM_BN", None)
-print("geglu N=2560 K=320:", round(bench(M, 2560, 320, geglu=True), 3), " plain N=2560 K=320 no-res:", round(bench(M, 2560, 320, res=False), 3), flush=True)
+def main():
+    M = 331776
+    for (N, K) in [(320, 320), (960, 320), (320, 1280)]:
+        for bn in ("", "128", "160", "256"):
+            if bn: os.environ["HV_GEMM_BN"] = bn
+            else: os.environ.pop("HV_GEMM_BN", None)
+            t_full = bench(M, N, K)
+            t_nores = bench(M, N, K, res=False)
+            t_nobias = bench(M, N, K, bias=False, res=False)
+            t_nostore = bench(M, N, K, bias=False, res=False, n_valid=8)
+            print(f"N={N} K={K} BN={bn or 'auto'}: full {t_full:.3f}  no-res {t_nores:.3f}  no-bias/res {t_nobias:.3f}  no-store {t_nostore:.3f} ms", flush=True)
+    os.environ.pop("HV_GEMM_BN", None)
+    print("geglu N=2560 K=320:", round(bench(M, 2560, 320, geglu=True), 3), " plain N=2560 K=320 no-res:", round(bench(M, 2560, 320, res=False), 3), flush=True)
+
+
+if __name__ == '__main__':
+    main()
