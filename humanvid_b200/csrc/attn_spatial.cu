@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -34,7 +35,11 @@ constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per tile
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is rescaled only when the row max grows by more than 2^8
 
-template <int D>
+// PT ("P in TMEM"): the probabilities never touch shared memory -- the softmax threads store them (packed fp16) into 64
+// TMEM columns and the P V MMA takes its A operand from there.  That frees 32 KB of shared memory (a third K/V stage), the
+// 32 KB of st.shared + the proxy fence per key tile, and the 32 KB the P V MMAs used to read back.  Needs 128 (S) + 64 (P)
+// + dv (O) <= 256 TMEM columns to keep two CTAs per SM, i.e. head dims up to 47.
+template <int D, bool PT = false>
 struct ACfg {
   static constexpr int kDpad = (D + 15) / 16 * 16;             // Q/K head stride (zero padded)
   static constexpr int kDv = (D + 1 + 15) / 16 * 16;           // V^T rows per head: d values, one row of ones, zero pad
@@ -43,11 +48,13 @@ struct ACfg {
   static constexpr int kKBytes = kKC * KT * 128;
   static constexpr int kVChunk = kDv * 128;                    // [dv rows][64 keys]
   static constexpr int kVBytes = 2 * kVChunk;
-  static constexpr int kPBytes = 2 * QT * 128;                 // two 64-key chunks
+  static constexpr int kPBytes = PT ? 0 : 2 * QT * 128;        // two 64-key chunks
   static constexpr int kStageBytes = kKBytes + kVBytes;
-  static constexpr int kStages = (kQBytes + kPBytes + 2 * kStageBytes + 2048 <= 227 * 1024) ? 2 : 1;
-  static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 128 + 2048 + 1024;  // + barriers, row-max exchange, alignment
-  static constexpr int kTmemCols = (128 + kDv) <= 256 ? 256 : 512;
+  static constexpr int kMisc = 256 + 2048 + 1024;               // barriers, row-max exchange, alignment
+  static constexpr int kStages = (PT && 2 * (kQBytes + 3 * kStageBytes + kMisc) <= 227 * 1024) ? 3
+                                 : (kQBytes + kPBytes + 2 * kStageBytes + 2048 <= 227 * 1024) ? 2 : 1;
+  static constexpr int kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + kMisc;
+  static constexpr int kTmemCols = (128 + (PT ? 64 : 0) + kDv) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = (2 * kSmemBytes <= 227 * 1024 && kTmemCols == 256) ? 2 : 1;
 };
 
@@ -57,6 +64,7 @@ struct AttnKernelArgs {
   int L, Lb, F, nf_nobank, heads;
   int vt_stride, vbt_stride;
   float scale_log2;
+  long long* dbg;   // PE == 31 only: per-CTA accumulated clock64() spans of the pipeline phases (16 slots per CTA)
 };
 
 template <int D>
@@ -375,12 +383,18 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 // memory and a 256-thread named barrier once per key tile.
 constexpr int ATT8_THREADS = 320;
 
-template <int D>
-__global__ void __launch_bounds__(ATT8_THREADS, ACfg<D>::kMinBlocks)
+// PE > 0: every PE-th pair of exponentials of a full 32-key chunk is evaluated on the FMA pipe (exp2_poly3) instead of MUFU.
+template <int D, int PE, bool PT>
+__global__ void __launch_bounds__(ATT8_THREADS, ACfg<D, PT>::kMinBlocks)
 attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
              const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
-  using C = ACfg<D>;
+  using C = ACfg<D, PT>;
+  auto WAIT = [](uint64_t* bar, uint32_t parity) {
+    if constexpr (PE == 21) mbar_wait_nohint(bar, parity);
+    else if constexpr (PE == 22) mbar_wait_poll(bar, parity);
+    else mbar_wait(bar, parity);
+  };
   constexpr int DP = C::kDpad, DV = C::kDv;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -393,10 +407,14 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   uint64_t* bar_pv = bars + 2;
   uint64_t* bar_s = bars + 3;        // [2]
   uint64_t* bar_sfree = bars + 5;    // [2]
-  uint64_t* bar_kv_full = bars + 7;
-  uint64_t* bar_kv_empty = bars + 7 + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * C::kStages);
-  float* smax = reinterpret_cast<float*>(bars + 16);   // [2 (tile parity)][2 (half)][128 rows]
+  // K and V tiles travel through separate rings: a K slot is free again as soon as its S = Q K^T has been computed (one
+  // key tile before the P V of the same tile), so K(j+2) is in flight a full tile earlier than a combined stage allows
+  uint64_t* bar_k_full = bars + 7;
+  uint64_t* bar_k_empty = bars + 7 + C::kStages;
+  uint64_t* bar_v_full = bars + 7 + 2 * C::kStages;
+  uint64_t* bar_v_empty = bars + 7 + 3 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 4 * C::kStages);
+  float* smax = reinterpret_cast<float*>(bars + 32);   // [2 (tile parity)][2 (half)][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT;
@@ -416,8 +434,10 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       mbar_init(&bar_sfree[hh], 128);
     }
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&bar_kv_full[s], 1);
-      mbar_init(&bar_kv_empty[s], 1);
+      mbar_init(&bar_k_full[s], 1);
+      mbar_init(&bar_k_empty[s], 1);
+      mbar_init(&bar_v_full[s], 1);
+      mbar_init(&bar_v_empty[s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&map_q);
@@ -430,7 +450,8 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_p = tmem_base + 128;                  // PT: 64 columns of packed fp16 probabilities (128 keys)
+  const uint32_t tmem_o = tmem_base + (PT ? 192 : 128);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -440,19 +461,21 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < T; ++j) {
-        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
         uint8_t* sK = sKV + stage * C::kStageBytes;
         uint8_t* sV = sK + C::kKBytes;
-        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
         const bool self = j < Ts;
         const CUtensorMap* mk = self ? &map_k : &map_kb;
         const CUtensorMap* mv = self ? &map_vt : &map_vbt;
         const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;
         const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;
+        mbar_wait(&bar_k_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bar_k_full[stage], C::kKBytes);
 #pragma unroll
-        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
-        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
-        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
+        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_k_full[stage], h * DP + kc * 64, tok);
+        mbar_wait(&bar_v_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bar_v_full[stage], C::kVBytes);
+        tma_load_2d(sV, mv, &bar_v_full[stage], vcol, h * DV);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_v_full[stage], vcol + 64, h * DV);
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -475,50 +498,78 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
 #pragma unroll
         for (int kk = 0; kk < KT / 16; ++kk) {
-          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
           const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
-          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          if constexpr (PT) {
+            umma_f16_ts(tmem_o, tmem_p + kk * 8, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
+            umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(bar_pv);
-        umma_commit(&bar_kv_empty[stage]);
+        umma_commit(&bar_v_empty[stage]);
       };
       int stage = 0;
       uint32_t phase = 0;
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv_full[0], 0);
+      constexpr bool kProf = PE == 31;
+      long long pt[6] = {0, 0, 0, 0, 0, 0}, pc = 0;
+      auto tick = [&](int slot) {
+        if constexpr (kProf) {
+          const long long now = clock64();
+          pt[slot] += now - pc;
+          pc = now;
+        }
+      };
+      WAIT(bar_q, 0);
+      WAIT(&bar_k_full[0], 0);
       tc_fence_after();
       issue_s_half(0, 0);
       issue_s_half(0, 1);
+      umma_commit(&bar_k_empty[0]);
+      if constexpr (kProf) pc = clock64();
       for (int j = 0; j < T; ++j) {
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == C::kStages) { nstage = 0; nphase ^= 1; }
         if constexpr (C::kStages >= 2) {
           if (j + 1 < T) {
-            mbar_wait(&bar_kv_full[nstage], nphase);
+            WAIT(&bar_k_full[nstage], nphase);
+            tick(0);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              mbar_wait(&bar_sfree[hh], j & 1);
+              WAIT(&bar_sfree[hh], j & 1);
               tc_fence_after();
+              tick(1 + hh);
               issue_s_half(nstage, hh);
+              tick(3);
             }
+            umma_commit(&bar_k_empty[nstage]);
           }
-          mbar_wait(bar_p, j & 1);
+          WAIT(bar_p, j & 1);
+          WAIT(&bar_v_full[stage], phase);
           tc_fence_after();
+          tick(4);
           issue_pv(stage, j);
+          tick(5);
         } else {
-          mbar_wait(bar_p, j & 1);
+          WAIT(bar_p, j & 1);
+          WAIT(&bar_v_full[stage], phase);
           tc_fence_after();
           issue_pv(stage, j);
           if (j + 1 < T) {
-            mbar_wait(&bar_kv_full[nstage], nphase);
+            WAIT(&bar_k_full[nstage], nphase);
             tc_fence_after();
             issue_s_half(nstage, 0);
             issue_s_half(nstage, 1);
+            umma_commit(&bar_k_empty[nstage]);
           }
         }
         stage = nstage;
         phase = nphase;
+      }
+      if constexpr (kProf) {
+        long long* d = a.dbg + (static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 24 + 12;
+        for (int i = 0; i < 6; ++i) d[i] = pt[i];
       }
     }
   } else {
@@ -533,15 +584,30 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int sw = r & 7;
     const float sc = a.scale_log2;
 
+    constexpr bool kProf = PE == 31;
+    long long pt[7] = {0, 0, 0, 0, 0, 0, 0}, pc = 0;
+    auto tick = [&](int slot) {
+      if constexpr (kProf) {
+        const long long now = clock64();
+        pt[slot] += now - pc;
+        pc = now;
+      }
+    };
+    if constexpr (kProf) pc = clock64();
     for (int j = 0; j < T; ++j) {
       const bool self = j < Ts;
       const int kv_valid = (self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT)) - hf * 64;   // valid keys in my half (may be <= 0)
-      mbar_wait(&bar_s[hf], j & 1);
+      WAIT(&bar_s[hf], j & 1);
       tc_fence_after();
+      tick(0);
       // pass 1: my half's row max
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      constexpr bool kDbgNoPass1 = PE == 11 || PE == 12;   // timing experiments only (results wrong)
+      constexpr bool kDbgNoSync = PE == 12;
+      constexpr bool kDbgNoExp = PE == 13;
+      if (kDbgNoPass1) mx0 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < (kDbgNoPass1 ? 0 : 2); ++c) {
         uint32_t raw[32];
         tmem_ld32(my_s + c * 32, raw);
         tmem_ld_wait();
@@ -557,14 +623,16 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
         }
       }
+      tick(1);
       float* sm = smax + (j & 1) * 256;
       sm[hf * 128 + r] = fmaxf(mx0, mx1) * sc;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!kDbgNoSync) asm volatile("bar.sync 1, 256;" ::: "memory");
+      tick(2);
       const float rowmax = fmaxf(sm[r], sm[128 + r]);
       const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
       const float m_new = grow ? rowmax : m_used;
       if (j > 0) {
-        mbar_wait(bar_pv, (j - 1) & 1);   // previous P V done: P smem and O are ours again
+        WAIT(bar_pv, (j - 1) & 1);   // previous P V done: P smem and O are ours again
         tc_fence_after();
         if (hf == 0 && __any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
@@ -581,6 +649,7 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
       }
       m_used = m_new;
+      tick(3);
       // pass 2: p = 2^(s*scale - m) -> fp16 -> my 64-key chunk of P
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -594,8 +663,12 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         uint32_t pk[16];
         if ((c + 1) * 32 <= kv_valid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)));
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = fmaf(__uint_as_float(raw[2 * i]), sc, -m_used), a1 = fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used);
+            if (kDbgNoExp) pk[i] = pack_h2(a0, a1);
+            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
+            else pk[i] = pack_h2(fast_exp2(a0), fast_exp2(a1));
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -605,16 +678,29 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             pk[i] = pack_h2(p0, p1);
           }
         }
+        if constexpr (PT) {
+          tmem_st16(tmem_p + lane_off + hf * 32 + c * 16, pk);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(prow + (((c * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(prow + (((c * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
       }
-      fence_proxy_async();
+      tick(4);
+      if constexpr (PT) tmem_st_wait();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_p);
+      tick(5);
+    }
+    if constexpr (kProf) {
+      if (threadIdx.x == 64 || threadIdx.x == 64 + 128) {   // warp 2 (half 0) and warp 6 (half 1), lane 0
+        long long* d = a.dbg + (static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 24 + (hf ? 6 : 0);
+        for (int i = 0; i < 6; ++i) d[i] = pt[i];
+      }
     }
     // epilogue: O / denominator; the two threads of a row write alternate 8-column groups
-    mbar_wait(bar_pv, (T - 1) & 1);
+    WAIT(bar_pv, (T - 1) & 1);
     tc_fence_after();
     float o[DV];
 #pragma unroll
@@ -930,6 +1016,44 @@ attn_kernel16(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   }
 }
 
+template <int D, int PE, bool PT>
+cudaError_t launch_attn8(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const CUtensorMap& mkb,
+                         const CUtensorMap& mvbt, AttnKernelArgs ka, int L, cudaStream_t stream) {
+  using C = ACfg<D, PT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel8<D, PE, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attn_kernel8<D, PE, PT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  if constexpr (PE == 31) {   // phase-timing experiment: blocking, prints the per-key-tile averages
+    const long long nct = static_cast<long long>(grid.x) * grid.y * grid.z;
+    if (cudaMalloc(&ka.dbg, nct * 24 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+    cudaMemsetAsync(ka.dbg, 0, nct * 24 * sizeof(long long), stream);
+    attn_kernel8<D, PE, PT><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    cudaStreamSynchronize(stream);
+    long long* h = static_cast<long long*>(malloc(nct * 24 * sizeof(long long)));
+    cudaMemcpy(h, ka.dbg, nct * 24 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double acc[24] = {0};
+    for (long long c = 0; c < nct; ++c)
+      for (int i = 0; i < 24; ++i) acc[i] += static_cast<double>(h[c * 24 + i]);
+    const double tiles = static_cast<double>(nct) * ((L + KT - 1) / KT);
+    const char* sn[6] = {"wait S", "pass1", "max xchg+bar", "wait PV(+rescale)", "pass2", "fence+arrive"};
+    const char* mn[6] = {"wait k_full", "wait sfree0", "wait sfree1", "issue S", "wait P,V", "issue PV"};
+    fprintf(stderr, "[attn8 phase clocks per key tile, D=%d L=%d PT=%d stages=%d]\n", D, L, (int)PT, C::kStages);
+    for (int i = 0; i < 6; ++i) fprintf(stderr, "  softmax h0 %-18s %8.1f   h1 %8.1f\n", sn[i], acc[i] / tiles, acc[6 + i] / tiles);
+    for (int i = 0; i < 6; ++i) fprintf(stderr, "  mma        %-18s %8.1f\n", mn[i], acc[12 + i] / tiles);
+    free(h);
+    cudaFree(ka.dbg);
+    return cudaGetLastError();
+  } else {
+    attn_kernel8<D, PE, PT><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    return cudaGetLastError();
+  }
+}
+
 template <int D>
 cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   using C = ACfg<D>;
@@ -948,7 +1072,12 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   }
   static bool attr = false;
   static int nwarps = 8;
+  static int mode = 0;      // HV_ATTN_POLY: 0 (default), 2 / 4 = polynomial exp2 on every 2nd / 4th pair, 13 / 31 = timing experiments
+  static int use_pt = 1;    // HV_ATTN_PT=0: keep P in shared memory even where it fits in TMEM
   if (!attr) {
+    if (const char* pv = getenv("HV_ATTN_POLY")) mode = atoi(pv);
+    if (mode != 0 && mode != 2 && mode != 4 && mode != 13 && mode != 31) mode = 0;
+    if (const char* pt = getenv("HV_ATTN_PT")) use_pt = atoi(pt);
     const char* ev = getenv("HV_ATTN_WARPS");
     if (ev) nwarps = atoi(ev);
     if (nwarps != 4 && nwarps != 8 && nwarps != 16) nwarps = 8;
@@ -959,10 +1088,6 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attn_kernel8<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attn_kernel8<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -977,11 +1102,28 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   ka.vt_stride = static_cast<int>(a.vt_stride);
   ka.vbt_stride = static_cast<int>(a.vbt_stride);
   ka.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
+  ka.dbg = nullptr;
   dim3 grid((a.L + QT - 1) / QT, a.heads, a.NF);
-  if (nwarps == 16) attn_kernel16<D><<<grid, ATT16_THREADS, A16Cfg<D>::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
-  else if (nwarps == 8) attn_kernel8<D><<<grid, ATT8_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
-  else attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
-  return cudaGetLastError();
+  if (nwarps == 16) {
+    attn_kernel16<D><<<grid, ATT16_THREADS, A16Cfg<D>::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    return cudaGetLastError();
+  }
+  if (nwarps == 4) {
+    attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    return cudaGetLastError();
+  }
+  constexpr bool kCanPT = 128 + 64 + C::kDv <= 256;
+  const bool pt = kCanPT && use_pt != 0;
+#define HV_ATT8(PE_)                                                                                                   \
+  (pt ? launch_attn8<D, PE_, kCanPT>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream) : launch_attn8<D, PE_, false>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream))
+  switch (mode) {
+    case 2: return HV_ATT8(2);
+    case 4: return HV_ATT8(4);
+    case 13: return HV_ATT8(13);
+    case 31: return HV_ATT8(31);
+    default: return HV_ATT8(0);
+  }
+#undef HV_ATT8
 }
 
 }  // namespace

@@ -26,7 +26,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB per 128-row sub-tile
-constexpr int kStagePerWarp = 128;  // per epilogue warp: its <= 64 bias values (LDS broadcast instead of an LDG per use)
+constexpr int kStagePerWarp = 256;  // per epilogue warp: its <= 64 bias values as fp32 (LDS broadcast instead of an LDG + convert per use)
 constexpr int kMaxStages = 8;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int GEMM_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
@@ -43,13 +43,17 @@ struct Cfg {
   static constexpr int kAccStages = (2 * MT * BLOCK_N <= 512) ? 2 : 1;
   static constexpr int kAccCols = MT * BLOCK_N;                         // TMEM columns per accumulator stage
   static constexpr int kTmemCols = kAccStages * kAccCols <= 256 ? 256 : 512;
-  static constexpr int kFixed = 16 * kStagePerWarp + 256 + 1024;         // epilogue staging + barriers + alignment slack
+  // per epilogue warp: a 32-row x BLOCK_N/4-column fp16 box through which its slice of the residual arrives and its slice
+  // of the output leaves by TMA (128-row tiles only; the 256-row conv tiles are compute-bound and keep direct stores)
+  static constexpr int kIoPerWarp = MT == 1 ? 32 * (BLOCK_N / 4) * 2 : 0;
+  static constexpr int kIoBytes = 16 * kIoPerWarp;
+  static constexpr int kBarBytes = (2 * kMaxStages + 6 + 16) * 8 + 16;  // full[8] empty[8] tfull[2] tempty[2] bpanel[2] res[16] + TMEM slot
+  static constexpr int kFixed = kIoBytes + kBarBytes + 16 * kStagePerWarp + 1024;  // + alignment slack
   static constexpr int kStagesFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kBarBytes = (2 * kMaxStages + 6) * 8 + 16;       // full[8] empty[8] tfull[2] tempty[2] bpanel[2] + TMEM slot
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 16 * kStagePerWarp + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   // B-stationary mode: the CTA's whole BLOCK_N x K weight panel stays in shared memory, the ring holds A tiles only
-  static constexpr int kBstFixed = kBarBytes + 16 * kStagePerWarp + 1024;
+  static constexpr int kBstFixed = kFixed;
 };
 
 struct TileCoord {
@@ -93,6 +97,15 @@ __device__ __forceinline__ void lds8(const __half* src, float* v) {  // shared m
     v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void ldsf8(const float* src, float* v) {  // shared memory, 16-byte aligned
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ void load8(const __half* src, float* v) {
   uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
   const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -111,7 +124,8 @@ __device__ __forceinline__ void load8(const __half* src, float* v) {
 template <int BLOCK_N, int MT, bool BST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-            const __grid_constant__ CUtensorMap map_b, const GemmProblem p, const GemmEpilogue e) {
+            const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+            const __grid_constant__ CUtensorMap map_res, const GemmProblem p, const GemmEpilogue e) {
   using C = Cfg<BLOCK_N, MT>;
   constexpr int TILE_M = MT * BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
@@ -119,12 +133,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int nstages = BST ? p.bst_stages : C::kStages;
   constexpr int kRingStageBytes = BST ? C::kATileBytes : C::kStageBytes;
   uint8_t* ring = smem + (BST ? p.num_k_blocks * C::kBTileBytes : 0);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + nstages * kRingStageBytes);
+  uint8_t* io_base = ring + nstages * kRingStageBytes;   // 1024-byte aligned (every ring stage is a multiple of 1 KB)
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(io_base + C::kIoBytes);
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_tfull = bar_empty + kMaxStages;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint64_t* bar_bpanel = bar_tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_bpanel + 2);
+  uint64_t* bar_res = bar_bpanel + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_res + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,6 +157,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(bar_bpanel, 1);
+    for (int s = 0; s < 16; ++s) mbar_init(&bar_res[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 16);
@@ -149,6 +166,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
+    if (e.tma_io) {
+      tma_prefetch_desc(&map_out);
+      tma_prefetch_desc(&map_res);
+    }
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
   tc_fence_before();
@@ -241,25 +262,172 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int q = warp & 3;             // TMEM lane quadrant this warp may read
     const int cs = (warp - 2) >> 2;     // column slice of the tile handled by this warp (0..3)
     const int r = q * 32 + lane;
-    __half* sbias = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + (warp - 2) * kStagePerWarp);
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + (warp - 2) * kStagePerWarp);
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
     constexpr int SL = BLOCK_N / 4;     // columns per warp slice: 64 / 40 / 32
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const TileCoord tc = tile_coord(p, m_blk, TILE_M);
       // this warp's slice of the bias vector -> its private shared-memory strip (issued before the wait on the accumulator)
       if (e.bias != nullptr) {
+        // lane l holds strip entries 2l, 2l+1: plain = this warp's SL columns; GEGLU = 32 hidden then their 32 gates
         int bcol;
         bool act;
-        if (!e.geglu) { bcol = n_blk * BLOCK_N + cs * SL + lane * 8; act = lane * 8 < SL; }
-        else { bcol = n_blk * BLOCK_N + cs * (BLOCK_N / 8) + (lane & 3) * 8 + (lane >> 2) * (BLOCK_N / 2); act = lane < 8; }  // 0-3 hidden, 4-7 gate
-        uint4 bv = make_uint4(0, 0, 0, 0);
-        if (act && p.b_batch == 0 && bcol < p.N) bv = __ldg(reinterpret_cast<const uint4*>(e.bias + bcol));
+        if (!e.geglu) { bcol = n_blk * BLOCK_N + cs * SL + lane * 2; act = lane * 2 < SL; }
+        else { bcol = n_blk * BLOCK_N + cs * (BLOCK_N / 8) + (lane & 15) * 2 + (lane >> 4) * (BLOCK_N / 2); act = true; }
+        float2 bv = make_float2(0.f, 0.f);
+        if (act && p.b_batch == 0 && bcol < p.N) bv = __half22float2(*reinterpret_cast<const __half2*>(e.bias + bcol));
         __syncwarp();
-        if (act) *reinterpret_cast<uint4*>(sbias + lane * 8) = bv;
+        if (act) *reinterpret_cast<float2*>(sbias + lane * 2) = bv;
         __syncwarp();
       }
+      const bool ts = MT == 1 && e.tma_io != 0;
+      int ts_col0 = 0, ts_row0 = 0;
+      uint8_t* io = io_base + (warp - 2) * C::kIoPerWarp;
+      if (ts) {
+        // ---- 128-row linear tiles: this warp's 32 x SL slice goes through its shared-memory box; the residual slice is
+        // fetched into the box by TMA while the MMAs run, updated in place (each thread touches only its own row) and
+        // the finished box leaves with one TMA store: full 128-byte lines instead of 16 bytes per thread and row.
+        constexpr int PITCH = SL * 2;                    // bytes per staged row: 128 / 80 / 64
+        const bool has_res = e.residual != nullptr && !e.geglu;
+        ts_row0 = tc.m0 + q * 32;
+        ts_col0 = e.geglu ? n_blk * (BLOCK_N / 2) + cs * (BLOCK_N / 8) : n_blk * BLOCK_N + cs * SL;
+        if (lane == 0) {
+          tma_store_wait_read();                         // the previous tile's store has drained the box
+          if (has_res) {
+            mbar_arrive_expect_tx(&bar_res[warp - 2], 32 * PITCH);
+            tma_load_2d(io, &map_res, &bar_res[warp - 2], ts_col0, ts_row0);
+          }
+        }
+        __syncwarp();
+        mbar_wait(&bar_tfull[acc], acc_phase);
+        tc_fence_after();
+        const long long row = tc.m0 + r;
+        const bool row_ok = row < p.M;
+        const __half* __restrict__ rv = (e.rowvec != nullptr && row_ok) ? e.rowvec + (row / e.rows_per_group) * e.rowvec_ld : nullptr;
+        const bool has_bias = e.bias != nullptr;
+        const float rowbias = (e.rowbias != nullptr && row_ok) ? __half2float(e.rowbias[row]) : 0.f;
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::kAccCols;
+        if (!e.geglu) {
+          constexpr int NC = (SL + 15) / 16;
+          const int colbase = ts_col0;
+          const int swz = PITCH == 128 ? (lane & 7) : PITCH == 64 ? ((lane >> 1) & 3) : 0;
+          uint8_t* myrow = io + lane * PITCH;
+          const bool lean = e.rowvec == nullptr && e.act == ACT_NONE && e.rowbias == nullptr;
+          uint32_t raw[2][16];
+          auto fetch = [&](int c, int buf) {
+            if (c * 16 + 16 <= SL) tmem_ld16(t_acc + cs * SL + c * 16, raw[buf]);
+            else tmem_ld8(t_acc + cs * SL + c * 16, raw[buf]);
+          };
+          fetch(0, 0);
+          if (has_res) {
+            mbar_wait(&bar_res[warp - 2], res_phase);
+            res_phase ^= 1;
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) fetch(c + 1, (c + 1) & 1);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int col = colbase + c * 16 + g * 8;
+              if (c * 16 + g * 8 < SL && col < e.n_valid) {
+                float v[8], t[8];
+                if (lean) {
+                  // bias -> fp16 (the linear's own output rounding) -> + residual in packed half arithmetic -> box
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]);
+                  if (has_bias) {
+                    ldsf8(sbias + c * 16 + g * 8, t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += t[i];
+                  }
+                  uint4 o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                  uint4* sp4 = reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4));
+                  if (has_res) {
+                    const uint4 rr = *sp4;
+                    o.x = hadd2_u32(o.x, rr.x);
+                    o.y = hadd2_u32(o.y, rr.y);
+                    o.z = hadd2_u32(o.z, rr.z);
+                    o.w = hadd2_u32(o.w, rr.w);
+                  }
+                  *sp4 = o;
+                  continue;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
+                if (has_bias) {
+                  ldsf8(sbias + c * 16 + g * 8, t);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += t[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
+                if (rv != nullptr) {
+                  load8(rv + col, t);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+                }
+                if (e.act == ACT_RELU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (e.act == ACT_SILU) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
+                }
+                __half* sp = reinterpret_cast<__half*>(myrow + (((2 * c + g) ^ swz) << 4));
+                if (has_res) {
+                  lds8(sp, t);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += t[i];
+                }
+                store8(sp, v);
+              }
+            }
+          }
+        } else {
+          constexpr int NC = (BLOCK_N / 8) / 16;
+          const int hcol0 = cs * (BLOCK_N / 8);
+          const int swz = (lane >> 1) & 3;               // 64-byte rows, 64B swizzle
+          uint8_t* myrow = io + lane * 64;
+          uint32_t hraw[2][16], graw[2][16];
+          auto fetch = [&](int c, int buf) {
+            tmem_ld16(t_acc + hcol0 + c * 16, hraw[buf]);
+            tmem_ld16(t_acc + BLOCK_N / 2 + hcol0 + c * 16, graw[buf]);
+          };
+          fetch(0, 0);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) fetch(c + 1, (c + 1) & 1);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float bh[8], bg[8];
+              if (has_bias) {
+                ldsf8(sbias + c * 16 + g * 8, bh);
+                ldsf8(sbias + 32 + c * 16 + g * 8, bg);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 h2 = __floats2half2_rn(__uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i],
+                                                     __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1]);
+                const float2 gf = __half22float2(__floats2half2_rn(__uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i],
+                                                                   __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1]));
+                const __half2 ge = __floats2half2_rn(gelu_erf_fast(gf.x), gelu_erf_fast(gf.y));
+                const __half2 pr = __hmul2(h2, ge);
+                o[i] = *reinterpret_cast<const uint32_t*>(&pr);
+              }
+              *reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+      } else {
       if (e.residual != nullptr && !e.geglu) {
         // pull this thread's residual row segments towards L2 while the tile's MMAs are still running
 #pragma unroll
@@ -338,7 +506,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
                 if (has_bias) {
-                  lds8(sbias + c * 16 + g * 8, t);
+                  ldsf8(sbias + c * 16 + g * 8, t);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] += t[i];
                 }
@@ -390,8 +558,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               const int ocol = n_blk * (BLOCK_N / 2) + hcol0 + c * 16 + g * 8;
               float bh[8], bg[8];
               if (has_bias) {
-                lds8(sbias + c * 16 + g * 8, bh);
-                lds8(sbias + 32 + c * 16 + g * 8, bg);
+                ldsf8(sbias + c * 16 + g * 8, bh);
+                ldsf8(sbias + 32 + c * 16 + g * 8, bg);
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) bh[i] = bg[i] = 0.f;
@@ -412,11 +580,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           }
         }
       }  // sub-tiles
+      }  // direct-store path
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      if (lane == 0) {
+        mbar_arrive(&bar_tempty[acc]);
+        if (ts) {
+          tma_store_2d(&map_out, io, ts_col0, ts_row0);
+          tma_store_commit();
+        }
+      }
       if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (MT == 1 && e.tma_io && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -451,22 +627,22 @@ void choose_conv_box(int NF, int H, int W, int* bn, int* bh, int* bw, int rows) 
 }
 
 template <int BN, int MT>
-static cudaError_t launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p, const GemmEpilogue& e,
-                            int grid, cudaStream_t stream) {
+static cudaError_t launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo, const CUtensorMap& mr,
+                            const GemmProblem& p, const GemmEpilogue& e, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::kSmemBytes);
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
-  gemm_kernel<BN, MT, false><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, p, e);
+  gemm_kernel<BN, MT, false><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, mo, mr, p, e);
   return cudaGetLastError();
 }
 
 // B-stationary launch; returns cudaErrorNotSupported when the shape does not qualify (caller falls back to the ring).
 template <int BN>
-static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmProblem p, const GemmEpilogue& e,
-                              int m_tiles, int n_tiles, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo, const CUtensorMap& mr,
+                              GemmProblem p, const GemmEpilogue& e, int m_tiles, int n_tiles, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, 1>;
   const int panel = p.num_k_blocks * C::kBTileBytes;
   int stages = (kMaxSmem - C::kBstFixed - panel) / C::kATileBytes;
@@ -481,12 +657,17 @@ static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, cons
   }
   p.bst_stages = stages;
   const int smem = panel + stages * C::kATileBytes + C::kBstFixed;
-  gemm_kernel<BN, 1, true><<<per_col * n_tiles, GEMM_THREADS, smem, stream>>>(a0, a1, b, p, e);
+  gemm_kernel<BN, 1, true><<<per_col * n_tiles, GEMM_THREADS, smem, stream>>>(a0, a1, b, mo, mr, p, e);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
-                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub) {
+                        const GemmEpilogue& e_in, int block_n, int num_sms, cudaStream_t stream, int m_sub, const CUtensorMap* io_out,
+                        const CUtensorMap* io_res) {
+  GemmEpilogue e = e_in;
+  e.tma_io = (io_out != nullptr && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && (e.residual == nullptr || e.geglu || io_res != nullptr)) ? 1 : 0;
+  const CUtensorMap& mo = e.tma_io ? *io_out : a0;
+  const CUtensorMap& mr = (e.tma_io && io_res) ? *io_res : mo;
   const int tile_m = BLOCK_M * m_sub;
   const int m_tiles = p.a_mode == A_LINEAR ? (p.M + tile_m - 1) / tile_m : p.tiles_n * p.tiles_y * p.tiles_x;
   const int n_tiles = p.b_batch ? p.b_batch * ((p.b_rows + block_n - 1) / block_n) : (p.N + block_n - 1) / block_n;
@@ -498,19 +679,19 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   static const int bst_env = [] { const char* v = getenv("HV_GEMM_BST"); return v ? atoi(v) : 1; }();
   if (bst_env && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && n_tiles <= num_sms) {
     cudaError_t r = cudaErrorNotSupported;
-    if (block_n == 256) r = launch_bst<256>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
-    if (block_n == 160) r = launch_bst<160>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
-    if (block_n == 128) r = launch_bst<128>(a0, a1, b, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (block_n == 256) r = launch_bst<256>(a0, a1, b, mo, mr, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (block_n == 160) r = launch_bst<160>(a0, a1, b, mo, mr, p, e, m_tiles, n_tiles, num_sms, stream);
+    if (block_n == 128) r = launch_bst<128>(a0, a1, b, mo, mr, p, e, m_tiles, n_tiles, num_sms, stream);
     if (r != cudaErrorNotSupported) return r;
   }
   if (m_sub == 1) {
-    if (block_n == 256) return launch_t<256, 1>(a0, a1, b, p, e, grid, stream);
-    if (block_n == 160) return launch_t<160, 1>(a0, a1, b, p, e, grid, stream);
-    if (block_n == 128) return launch_t<128, 1>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 256) return launch_t<256, 1>(a0, a1, b, mo, mr, p, e, grid, stream);
+    if (block_n == 160) return launch_t<160, 1>(a0, a1, b, mo, mr, p, e, grid, stream);
+    if (block_n == 128) return launch_t<128, 1>(a0, a1, b, mo, mr, p, e, grid, stream);
   } else if (m_sub == 2) {
-    if (block_n == 256) return launch_t<256, 2>(a0, a1, b, p, e, grid, stream);
-    if (block_n == 160) return launch_t<160, 2>(a0, a1, b, p, e, grid, stream);
-    if (block_n == 128) return launch_t<128, 2>(a0, a1, b, p, e, grid, stream);
+    if (block_n == 256) return launch_t<256, 2>(a0, a1, b, mo, mr, p, e, grid, stream);
+    if (block_n == 160) return launch_t<160, 2>(a0, a1, b, mo, mr, p, e, grid, stream);
+    if (block_n == 128) return launch_t<128, 2>(a0, a1, b, mo, mr, p, e, grid, stream);
   }
   return cudaErrorInvalidValue;
 }

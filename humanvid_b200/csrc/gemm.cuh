@@ -24,6 +24,7 @@ struct GemmEpilogue {
   int geglu = 0;                   // BLOCK_N=256 tile = [128 hidden | 128 gate] -> 128 outputs
   const __half* rowbias = nullptr; // [M]: added to every column of output row m (the "ones" rows of V^T)
   float* gn_stats = nullptr;       // reserved (fused GroupNorm statistics)
+  int tma_io = 0;                  // output tile leaves (and the residual tile arrives) through per-warp shared-memory boxes + TMA
 };
 
 struct GemmProblem {
@@ -45,8 +46,13 @@ struct GemmProblem {
 // C[M, N] = A[M, K] * B[N, K]^T  (fp16 in, fp32 accumulate in TMEM, fused epilogue, fp16 out).
 // a0/a1: TMA maps of the A operand (see make_* helpers in tma.h), b: TMA map of the packed weights [N][K].
 // block_n must be 128, 160 or 256 (256 required for geglu); 160 = two exact tiles for the 320-wide layers.
+// io_out / io_res (optional, linear A only, m_sub == 1): maps from make_map_2d_io with box 32 rows x gemm_io_box_cols(); when given,
+// the epilogue stages each warp's 32-row slice in shared memory and moves it with TMA (full-line stores instead of one
+// 16-byte fragment per thread and row).
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
-                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub = 1);
+                        const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub = 1,
+                        const CUtensorMap* io_out = nullptr, const CUtensorMap* io_res = nullptr);
+inline int gemm_io_box_cols(int block_n, bool geglu) { return geglu ? block_n / 8 : block_n / 4; }
 
 // Picks the (bn, bh, bw) output-tile box with the least padding for an NF x H x W output.
 // (rows = 128 or 256 output pixels per CTA tile; every box dimension is a power of two <= 256)

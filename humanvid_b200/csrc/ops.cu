@@ -123,7 +123,21 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   p.k_split = split ? static_cast<int>(K1 / 64) : 0;
   GemmEpilogue e;
   fill_epilogue(e, ep, out, ldc, N);
-  cudaError_t err = launch_gemm(ma0, ma1, mb, p, e, bn, sms, stream, m_sub);
+  // 128-row tiles: the output (and residual) slices move by TMA through per-warp shared-memory boxes
+  CUtensorMap mo, mr;
+  const CUtensorMap *pmo = nullptr, *pmr = nullptr;
+  static const int tma_io_env = [] { const char* v = getenv("HV_GEMM_TMA_IO"); return v ? atoi(v) : 1; }();
+  if (m_sub == 1 && tma_io_env) {
+    const int bc = gemm_io_box_cols(bn, geglu);
+    if (!make_map_2d_io(&mo, out, M, e.n_valid, ldc, 32, bc)) { set_error("hv_op_gemm out map: %s", tma_last_error()); return HV_ERR_TMA; }
+    pmo = &mo;
+    if (e.residual != nullptr && !geglu) {
+      if (e.ldr % 8) { set_error("hv_op_gemm: residual ld %d must be a multiple of 8", e.ldr); return HV_ERR_INVALID; }
+      if (!make_map_2d_io(&mr, e.residual, M, e.n_valid, e.ldr, 32, bc)) { set_error("hv_op_gemm residual map: %s", tma_last_error()); return HV_ERR_TMA; }
+      pmr = &mr;
+    }
+  }
+  cudaError_t err = launch_gemm(ma0, ma1, mb, p, e, bn, sms, stream, m_sub, pmo, pmr);
   if (err != cudaSuccess) return cuda_fail(err, "hv_op_gemm launch");
   return HV_OK;
 }

@@ -62,6 +62,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// try_wait without a suspend hint (implementation-default time limit), re-probed until the phase completes
+__device__ __forceinline__ void mbar_wait_nohint(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "HV_WAITN_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra HV_DONEN_%=;\n\t"
+      "bra HV_WAITN_%=;\n\t"
+      "HV_DONEN_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// pure polling (test_wait never suspends): lowest wake-up latency, costs issue slots
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "HV_WAITP_%=:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra HV_DONEP_%=;\n\t"
+      "bra HV_WAITP_%=;\n\t"
+      "HV_DONEP_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -92,6 +121,18 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+
+// TMA store: shared -> global, bulk-group completion (the issuing thread commits / waits)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -137,6 +178,15 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes (rows) x 8 columns holding 16 packed fp16 K-elements per row.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05 ops of this thread have completed.
@@ -204,19 +254,31 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// erf-GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the fp16 rounding that follows)
+// erf-GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the fp16 rounding that follows).
+// 0.5x(1 + erf(x/sqrt2)) = relu(x) - |x| * 0.5 erfc(|x|/sqrt2); the 0.5 is folded into the polynomial.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfc_abs = poly * t * fast_exp2(-z * z * 1.4426950408889634f);   // 1 - erf(|x|/sqrt2)
-  const float hx = 0.5f * x;
-  // 0.5x(1 + sign(x) erf) = x - 0.5x*erfc for x >= 0, 0.5x*erfc for x < 0
-  return x >= 0.f ? fmaf(-hx, erfc_abs, x) : hx * erfc_abs;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f)));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float e = fast_exp2(x * x * (-0.5f * 1.4426950408889634f));     // exp(-x^2 / 2)
+  const float q = poly * t * e * x;                                       // 0.5 x erfc(|x|/sqrt2), carries the sign of x
+  return fmaxf(x, 0.f) - fabsf(q);
+}
+
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], relative error 7.5e-5: a third of the fp16
+// half-ulp of the probabilities it produces).  Used for a fraction of the softmax exponentials so that the 16-lane
+// MUFU pipe is not the only unit doing them.
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -126.f);
+  const float fi = x + 12582912.f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (fi - 12582912.f);
+  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(fi) << 23));
 }
 
 }  // namespace hv

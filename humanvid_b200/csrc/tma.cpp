@@ -20,7 +20,7 @@ void resolve() {
 }
 
 bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-            const cuuint32_t* box) {
+            const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   std::call_once(g_once, resolve);
   if (!g_encode) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point not available");
@@ -28,7 +28,7 @@ bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, c
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u ptr %p", (int)r,
@@ -47,6 +47,14 @@ bool make_map_2d_box(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   return encode(m, ptr, 2, dims, strides, box);
+}
+
+bool make_map_2d_io(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return encode(m, ptr, 2, dims, strides, box, swz);
 }
 
 bool make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {

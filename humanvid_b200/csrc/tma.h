@@ -25,6 +25,11 @@ bool make_map_nhwc_s2(CUtensorMap* m, const void* ptr, int64_t N, int64_t H, int
 // even when the next batch item follows in memory.
 bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
+// Epilogue I/O box of the GEMM (TMA store of the output tile / TMA load of the residual tile): fp16 [rows][ld] with `cols`
+// valid columns, box = box_rows x box_cols, shared-memory rows of box_cols * 2 bytes (128 -> 128B swizzle, 64 -> 64B swizzle,
+// anything else unswizzled).  Out-of-range rows / columns are clipped on store and read as zero on load.
+bool make_map_2d_io(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+
 const char* tma_last_error();
 
 }  // namespace hv

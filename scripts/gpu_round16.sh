@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -p no:cacheprovider -x > gpurun_out/pytest_ops.log 2>&1
+echo "== pytest ops exit $?"; tail -3 gpurun_out/pytest_ops.log
+timeout -s KILL 300 python scripts/gemm_bst_ab.py > gpurun_out/lean.log 2>&1; echo "== gemm exit $?"; cat gpurun_out/lean.log | tail -10
+HV_TRACE=gpurun_out/trace_16.txt timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_16.log 2>&1
+echo "== bench exit $?"; tail -n 1 gpurun_out/bench_16.log | cut -c1-200; tail -n 1 gpurun_out/bench_16.log | grep -o '"op_profile.*' | cut -c1-900
+timeout -s KILL 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider -x > gpurun_out/pytest_model.log 2>&1
+echo "== pytest model exit $?"; tail -3 gpurun_out/pytest_model.log
