@@ -1016,6 +1016,386 @@ attn_kernel16(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "Ping-pong" variant for head dims < 48: ONE CTA per SM works on TWO 128-query tiles (groups A and B) of the same
+// (frame, head) against one shared K/V stream.  What the per-phase clocks of attn_kernel8 showed: a tcgen05.mma of this size
+// costs ~50 clocks to issue and ~300 to drain whatever its N, so S = Q K^T (6 MMAs) and P V (8 MMAs) put ~1100 clocks of
+// pure latency between the end of one tile's exponentials and the start of the next tile's; two independent CTAs per SM
+// fall into lockstep (both in the MUFU phase, then both waiting) instead of filling each other's gaps.  Here the two
+// groups are forced out of phase: a token (two named barriers) lets only one group at a time into its MUFU phase, so one
+// group's max / S / P V latency always hides behind the other group's exponentials, and the K/V tiles are fetched once
+// for 256 queries.  TMEM (512 columns): per group 128 S + 64 P (packed fp16, A operand of the P V MMA) + dv O.
+constexpr int ATTPP_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax A, warps 10-17 softmax B
+
+template <int D>
+struct PPCfg {
+  static constexpr int kDpad = (D + 15) / 16 * 16;
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;
+  static constexpr int kKC = (kDpad + 63) / 64;
+  static constexpr int kQBytes = kKC * QT * 128;                // one 128-query tile
+  static constexpr int kKBytes = kKC * KT * 128;
+  static constexpr int kVChunk = kDv * 128;
+  static constexpr int kVBytes = 2 * kVChunk;
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kMisc = kBarBytes + 4096 + 1024;          // barriers, row-max exchange (2 groups), alignment
+  static constexpr int kStagesFit = (227 * 1024 - 2 * kQBytes - kMisc) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kSmemBytes = 2 * kQBytes + kStages * kStageBytes + kMisc;
+  static constexpr bool kFits = 192 + kDv <= 256 && kStages >= 2;
+};
+
+template <int D, int PE, bool TOKEN>
+__global__ void __launch_bounds__(ATTPP_THREADS, 1)   // 18 warps -> 5 on two of the four schedulers -> 16K / (5 * 32) = 102 -> 96 registers
+attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
+               const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
+  using C = PPCfg<D>;
+  constexpr int DP = C::kDpad, DV = C::kDv, NS = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2 groups][kQBytes]
+  uint8_t* sKV = sQ + 2 * C::kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NS * C::kStageBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_s = bars + 1;        // [2]  S of group g is in TMEM
+  uint64_t* bar_sfree = bars + 3;    // [2]  all 256 threads of group g have read S
+  uint64_t* bar_p = bars + 5;        // [2]  P of group g is in TMEM
+  uint64_t* bar_pv = bars + 7;       // [2]  P V of group g has been accumulated
+  uint64_t* bar_k_full = bars + 9;
+  uint64_t* bar_k_empty = bars + 9 + NS;
+  uint64_t* bar_v_full = bars + 9 + 2 * NS;
+  uint64_t* bar_v_empty = bars + 9 + 3 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 4 * NS);
+  float* smax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);   // [2 groups][2 parity][2 halves][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * QT;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
+  const int Ts = (a.L + KT - 1) / KT;
+  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
+  const int bidx = n / a.F;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bar_s[g], 1);
+      mbar_init(&bar_sfree[g], 256);
+      mbar_init(&bar_p[g], 256);
+      mbar_init(&bar_pv[g], 1);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&bar_k_full[s], 1);
+      mbar_init(&bar_k_empty[s], 1);
+      mbar_init(&bar_v_full[s], 1);
+      mbar_init(&bar_v_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // group g: S at +256g (128 columns), P at +256g+128 (64), O at +256g+192 (DV)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, 2 * C::kQBytes);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int kc = 0; kc < C::kKC; ++kc)
+          tma_load_2d(sQ + g * C::kQBytes + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0 + g * QT);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        uint8_t* sK = sKV + stage * C::kStageBytes;
+        uint8_t* sV = sK + C::kKBytes;
+        const bool self = j < Ts;
+        const CUtensorMap* mk = self ? &map_k : &map_kb;
+        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
+        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;
+        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;
+        mbar_wait(&bar_k_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bar_k_full[stage], C::kKBytes);
+#pragma unroll
+        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_k_full[stage], h * DP + kc * 64, tok);
+        mbar_wait(&bar_v_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bar_v_full[stage], C::kVBytes);
+        tma_load_2d(sV, mv, &bar_v_full[stage], vcol, h * DV);
+        tma_load_2d(sV + C::kVChunk, mv, &bar_v_full[stage], vcol + 64, h * DV);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    {   // all 32 lanes run the issue loop with warp-uniform operands; one elected lane issues (see umma_*_w)
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
+      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
+      auto issue_s = [&](int g, int stage) {
+        const uint32_t aQ = smem_u32(sQ + g * C::kQBytes);
+        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
+          umma_f16_ss_w(tmem_base + g * 256, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit_w(&bar_s[g]);
+      };
+      auto issue_pv = [&](int g, int stage, int j) {
+        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
+          umma_f16_ts_w(tmem_base + g * 256 + 192, tmem_base + g * 256 + 128 + kk * 8, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit_w(&bar_pv[g]);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit_w(&bar_k_empty[0]);
+      for (int j = 0; j < T; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == NS) { nstage = 0; nphase ^= 1; }
+        const bool more = j + 1 < T;
+        if (more) mbar_wait(&bar_k_full[nstage], nphase);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (more) {
+            mbar_wait(&bar_sfree[g], j & 1);
+            tc_fence_after();
+            issue_s(g, nstage);
+            if (g == 1) umma_commit_w(&bar_k_empty[nstage]);
+          }
+          mbar_wait(&bar_p[g], j & 1);
+          if (g == 0) mbar_wait(&bar_v_full[stage], phase);
+          tc_fence_after();
+          issue_pv(g, stage, j);
+          if (g == 1) umma_commit_w(&bar_v_empty[stage]);
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: group g, two threads per query row
+    const int g = (warp - 2) >> 3;
+    const int w = (warp - 2) & 7;
+    const int qd = warp & 3;                        // TMEM lane quadrant of this warp
+    const int hf = w >> 2;                          // which 64-key half of every tile this thread owns
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 256, tmem_p = tmem_s + 128, tmem_o = tmem_s + 192;
+    const uint32_t my_s = tmem_s + lane_off + hf * 64;
+    float* gmax = smax + g * 512;
+    float m_used = -INFINITY;
+    const float sc = a.scale_log2;
+    // token: barrier 3 = "A may run its MUFU phase", barrier 4 = "B may"; B hands A the first turn
+    if (TOKEN && g == 1) asm volatile("bar.arrive 3, 512;" ::: "memory");
+    constexpr bool kProf = PE == 31;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+    auto tick = [&](int slot) {
+      if constexpr (kProf) {
+        const long long now = clock64();
+        pt[slot] += now - pc;
+        pc = now;
+      }
+    };
+    if constexpr (kProf) pc = clock64();
+
+    for (int j = 0; j < T; ++j) {
+      const bool self = j < Ts;
+      const int kv_valid = (self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT)) - hf * 64;
+      mbar_wait(&bar_s[g], j & 1);
+      tc_fence_after();
+      tick(0);
+      // pass 1: my half's row max.  The second 32-key chunk stays in registers for pass 2; the first is re-read from
+      // TMEM, the load being issued here so that its latency hides behind the row-max exchange.
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      uint32_t raw0[32], raw1[32];
+      tmem_ld32(my_s, raw0);
+      tmem_ld32(my_s + 32, raw1);
+      tmem_ld_wait();
+      if (64 <= kv_valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(raw0[i]), __uint_as_float(raw1[i])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(raw0[i + 1]), __uint_as_float(raw1[i + 1])));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw0[i]));
+          if (32 + i < kv_valid) mx1 = fmaxf(mx1, __uint_as_float(raw1[i]));
+        }
+      }
+      tick(1);
+      tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
+      float* sm = gmax + (j & 1) * 256;
+      sm[hf * 128 + r] = fmaxf(mx0, mx1) * sc;
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float rowmax = fmaxf(sm[r], sm[128 + r]);
+      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
+      const float m_new = grow ? rowmax : m_used;
+      tick(2);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_sfree[g]);   // all my reads of S are done: the MMA warp may overwrite it with the next tile's scores
+      if (j > 0) {
+        mbar_wait(&bar_pv[g], (j - 1) & 1);   // previous P V done: P and O are ours again
+        tc_fence_after();
+        if (hf == 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < DV / 16; ++c) {
+            uint32_t t16[16];
+            tmem_ld16(tmem_o + lane_off + c * 16, t16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
+            tmem_st16(tmem_o + lane_off + c * 16, t16);
+          }
+          tmem_st_wait();
+        }
+      }
+      m_used = m_new;
+      tick(3);
+      if (TOKEN) {
+        if (g == 0) asm volatile("bar.sync 3, 512;" ::: "memory");
+        else asm volatile("bar.sync 4, 512;" ::: "memory");
+      }
+      tick(4);
+      // pass 2: p = 2^(s*scale - m) -> packed fp16 -> my 32 columns of P
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t (&raw)[32] = c == 0 ? raw0 : raw1;
+        uint32_t pk[16];
+        if ((c + 1) * 32 <= kv_valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = fmaf(__uint_as_float(raw[2 * i]), sc, -m_used), a1 = fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used);
+            if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
+            else pk[i] = pack_h2(fast_exp2(a0), fast_exp2(a1));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = c * 32 + 2 * i;
+            const float p0 = c0 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)) : 0.f;
+            const float p1 = c0 + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)) : 0.f;
+            pk[i] = pack_h2(p0, p1);
+          }
+        }
+        tmem_st16(tmem_p + lane_off + hf * 32 + c * 16, pk);
+      }
+      tick(5);
+      if (TOKEN) {   // hand the MUFU phase to the other group (B's last turn has no taker)
+        if (g == 0) asm volatile("bar.arrive 4, 512;" ::: "memory");
+        else if (j + 1 < T) asm volatile("bar.arrive 3, 512;" ::: "memory");
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_p[g]);
+      tick(6);
+    }
+    if constexpr (kProf) {
+      if (lane == 0 && (w == 0 || w == 4)) {
+        long long* d = a.dbg + (static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 32 + g * 16 + (hf ? 8 : 0);
+        for (int i = 0; i < 7; ++i) d[i] = pt[i];
+      }
+    }
+    // epilogue: O / denominator; the two threads of a row write alternate 8-column groups
+    mbar_wait(&bar_pv[g], (T - 1) & 1);
+    tc_fence_after();
+    float o[DV];
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t raw16[16];
+      tmem_ld16(tmem_o + lane_off + c * 16, raw16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw16[i]);
+    }
+    tc_fence_before();
+    const int qrow = q0 + g * QT + r;
+    if (qrow < a.L) {
+      const float inv = 1.f / o[D];
+      __half* dst = a.out + (static_cast<long long>(n) * a.L + qrow) * a.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        if ((c & 1) == hf) {
+          uint4 u;
+          u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+          u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+          u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+          u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, int PE, bool TOKEN>
+cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const CUtensorMap& mkb, const CUtensorMap& mvbt,
+                           const AttnKernelArgs& ka, int L, int heads, int NF, cudaStream_t stream) {
+  using C = PPCfg<D>;
+  if constexpr (!C::kFits) {
+    return cudaErrorInvalidValue;
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<D, PE, TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      if (e != cudaSuccess) return e;
+      attr = true;
+    }
+    dim3 grid((L + 2 * QT - 1) / (2 * QT), heads, NF);
+    if constexpr (PE == 31) {   // phase-timing experiment: blocking, prints per-key-tile averages
+      AttnKernelArgs kd = ka;
+      const long long nct = static_cast<long long>(grid.x) * grid.y * grid.z;
+      if (cudaMalloc(&kd.dbg, nct * 32 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+      cudaMemsetAsync(kd.dbg, 0, nct * 32 * sizeof(long long), stream);
+      attn_pp_kernel<D, PE, TOKEN><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
+      cudaStreamSynchronize(stream);
+      long long* hb = static_cast<long long*>(malloc(nct * 32 * sizeof(long long)));
+      cudaMemcpy(hb, kd.dbg, nct * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+      double acc[32] = {0};
+      for (long long c = 0; c < nct; ++c)
+        for (int i = 0; i < 32; ++i) acc[i] += static_cast<double>(hb[c * 32 + i]);
+      const double tiles = static_cast<double>(nct) * ((L + KT - 1) / KT);
+      const char* sn[7] = {"wait S", "pass1 (ld+max)", "max xchg+bar", "ld wait+PV wait", "wait token", "pass2", "handoff+st+arrive"};
+      fprintf(stderr, "[attn_pp phase clocks per key tile, D=%d L=%d token=%d stages=%d]\n", D, L, (int)TOKEN, C::kStages);
+      for (int i = 0; i < 7; ++i)
+        fprintf(stderr, "  %-18s A.h0 %7.1f  A.h1 %7.1f  B.h0 %7.1f  B.h1 %7.1f\n", sn[i], acc[i] / tiles, acc[8 + i] / tiles, acc[16 + i] / tiles, acc[24 + i] / tiles);
+      free(hb);
+      cudaFree(kd.dbg);
+      return cudaGetLastError();
+    }
+    attn_pp_kernel<D, PE, TOKEN><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    return cudaGetLastError();
+  }
+}
+
 template <int D, int PE, bool PT>
 cudaError_t launch_attn8(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const CUtensorMap& mkb,
                          const CUtensorMap& mvbt, AttnKernelArgs ka, int L, cudaStream_t stream) {
@@ -1111,6 +1491,15 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   if (nwarps == 4) {
     attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
     return cudaGetLastError();
+  }
+  static const int pp_mode = [] { const char* v = getenv("HV_ATTN_PP"); return v ? atoi(v) : 2; }();  // 0 off, 1 token hand-off, 2 free-running groups (default: ~8 % fewer clocks than attn_kernel8 in the network)
+  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 4 || mode == 31)) {
+    if (mode == 31) return pp_mode == 2 ? launch_attn_pp<D, 31, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
+                                        : launch_attn_pp<D, 31, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (pp_mode == 2) return launch_attn_pp<D, 0, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mode == 4) return launch_attn_pp<D, 4, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mode == 2) return launch_attn_pp<D, 2, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    return launch_attn_pp<D, 0, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
   }
   constexpr bool kCanPT = 128 + 64 + C::kDv <= 256;
   const bool pt = kCanPT && use_pt != 0;
