@@ -107,6 +107,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
+def pick_cpu_threads():
+    """Thread count for the CPU arm: the fastest of a few candidates on a probe of the path's two dominant CPU ops (3x3 conv
+    and token GEMM at level-0 shape).  "All logical CPUs" is not it on the GPU boxes: 128 threads ran the oracle 10x slower
+    than 16 threads do on an 8-core container (OpenMP oversubscription under a CPU quota)."""
+    import torch
+    import torch.nn.functional as Fn
+
+    ncpu = os.cpu_count() or 1
+    try:
+        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    cands = sorted({c for c in (ncpu, 96, 64, 48, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    x = torch.randn(1, 320, H // 2, W // 2)
+    w = torch.randn(320, 320, 3, 3) * 0.02
+    a = torch.randn(H * W // 4, 1280)
+    b = torch.randn(1280, 1280) * 0.02
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            Fn.conv2d(x, w, padding=1); a @ b   # warm
+            t0 = time.perf_counter()
+            for _ in range(2):
+                Fn.conv2d(x, w, padding=1)
+                a @ b
+            t = time.perf_counter() - t0
+        if t < best_t * 0.95:   # prefer more threads only when clearly faster
+            best, best_t = c, t
+    return best
+
+
 def cpu_reference_sample(steps, warmup, frames=1, cfg_batch=1):
     """Oracle (reference-equivalent PyTorch, fp32) on the host cores.  One sample = UNet forward over `frames` frames of
     `cfg_batch` CFG halves at the full 96x72 latent: frames * cfg_batch of the step's 48 frame-passes (~30 s on 128 cores, the
@@ -115,8 +147,9 @@ def cpu_reference_sample(steps, warmup, frames=1, cfg_batch=1):
 
     from oracle import hv_oracle as O
 
-    nthreads = os.cpu_count() or 1
+    nthreads = pick_cpu_threads()
     torch.set_num_threads(nthreads)
+    torch.set_flush_denormal(True)   # random-init activations reach denormals in places; the x86 slow path would understate the CPU
     m = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval()
     synthetic_init_(m, 7, "cpu")
     g = torch.Generator().manual_seed(1)
@@ -135,7 +168,8 @@ def cpu_reference_sample(steps, warmup, frames=1, cfg_batch=1):
     passes = frames * cfg_batch
     return {"frames_per_s": 0.5 * passes / t, "s_per_sample": t, "cores": nthreads,
             "sample": f"UNet forward on {passes} of the step's 48 frame-passes ({frames} frame(s) x {cfg_batch} CFG half) at the full 96x72 latent, "
-                      f"fp32, {nthreads} threads, {len(times)} timed sample(s) of {t:.1f} s; frames/s = ({passes} / 2) / t"}
+                      f"fp32, {nthreads} threads (fastest of a thread-count probe), denormals flushed, {len(times)} timed sample(s) of {t:.1f} s; "
+                      f"frames/s = ({passes} / 2) / t"}
 
 
 def run_reference(args, rank):

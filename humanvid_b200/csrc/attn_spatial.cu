@@ -480,7 +480,7 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes, warp-uniform operands, one elected lane issues (see umma_*_w)
       constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       constexpr uint32_t idesc_sh = umma_idesc_f16(QT, KT / 2);
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
@@ -490,9 +490,9 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         for (int ks = 0; ks < DP / 16; ++ks) {
           const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
           const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
-          umma_f16_ss(tmem_s + hh * (KT / 2), ad, bd, idesc_sh, ks != 0 ? 1u : 0u);
+          umma_f16_ss_w(tmem_s + hh * (KT / 2), ad, bd, idesc_sh, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&bar_s[hh]);
+        umma_commit_w(&bar_s[hh]);
       };
       auto issue_pv = [&](int stage, int j) {
         const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
@@ -500,14 +500,14 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         for (int kk = 0; kk < KT / 16; ++kk) {
           const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
           if constexpr (PT) {
-            umma_f16_ts(tmem_o, tmem_p + kk * 8, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            umma_f16_ts_w(tmem_o, tmem_p + kk * 8, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
           } else {
             const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
-            umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            umma_f16_ss_w(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(bar_pv);
-        umma_commit(&bar_v_empty[stage]);
+        umma_commit_w(bar_pv);
+        umma_commit_w(&bar_v_empty[stage]);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -525,7 +525,7 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       tc_fence_after();
       issue_s_half(0, 0);
       issue_s_half(0, 1);
-      umma_commit(&bar_k_empty[0]);
+      umma_commit_w(&bar_k_empty[0]);
       if constexpr (kProf) pc = clock64();
       for (int j = 0; j < T; ++j) {
         int nstage = stage + 1;
@@ -543,7 +543,7 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
               issue_s_half(nstage, hh);
               tick(3);
             }
-            umma_commit(&bar_k_empty[nstage]);
+            umma_commit_w(&bar_k_empty[nstage]);
           }
           WAIT(bar_p, j & 1);
           WAIT(&bar_v_full[stage], phase);
@@ -561,13 +561,13 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             tc_fence_after();
             issue_s_half(nstage, 0);
             issue_s_half(nstage, 1);
-            umma_commit(&bar_k_empty[nstage]);
+            umma_commit_w(&bar_k_empty[nstage]);
           }
         }
         stage = nstage;
         phase = nphase;
       }
-      if constexpr (kProf) {
+      if constexpr (kProf) if (lane == 0) {
         long long* d = a.dbg + (static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 24 + 12;
         for (int i = 0; i < 6; ++i) d[i] = pt[i];
       }

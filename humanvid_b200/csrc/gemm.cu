@@ -222,8 +222,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: all 32 lanes run the loop with
+    // warp-uniform operands, one elected lane issues (umma_*_w) -- keeps the descriptors in uniform registers
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -244,12 +245,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const uint64_t adesc = umma_desc_k_sw128(sa + mt * A_TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_f16_ss(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_ss_w(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bar_empty[stage]);
+          umma_commit_w(&bar_empty[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bar_tfull[acc]);
+        umma_commit_w(&bar_tfull[acc]);
         if (++acc == C::kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -68,6 +68,13 @@ bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, i
   return encode(m, ptr, 3, dims, strides, box);
 }
 
+bool make_map_frames(CUtensorMap* m, const void* ptr, int64_t frames, int64_t pixels, int64_t cols, int64_t ld, int box_cols, int box_frames) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)pixels, (cuuint64_t)frames};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)pixels * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_frames};
+  return encode(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 bool make_map_nhwc(CUtensorMap* m, const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C, int bn, int bh, int bw) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};

@@ -30,6 +30,10 @@ bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, i
 // anything else unswizzled).  Out-of-range rows / columns are clipped on store and read as zero on load.
 bool make_map_2d_io(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
+// Token matrix [frames][pixels][ld] (cols valid) viewed along the frame axis: 3-D map (cols, pixels, frames), unswizzled box
+// (box_cols, 1, box_frames) = the box_frames rows of ONE pixel, box_cols channels wide (temporal attention operands).
+bool make_map_frames(CUtensorMap* m, const void* ptr, int64_t frames, int64_t pixels, int64_t cols, int64_t ld, int box_cols, int box_frames);
+
 const char* tma_last_error();
 
 }  // namespace hv

@@ -184,6 +184,21 @@ def test_temporal_attention(d, Fr):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("d,Fr,HW", [(40, 24, 300), (80, 24, 300), (40, 8, 700), (40, 32, 300), (80, 5, 1100), (40, 17, 301)])
+def test_temporal_attention_tma_staged(d, Fr, HW):
+    """>= 4096 (pixel, head) problems at d = 40 / 80: the TMA-staged kernel (per-warp shared-memory slabs, ldmatrix fragments)."""
+    B, heads = 2, 8
+    Cc = heads * d
+    qkv = dev(B * Fr * HW, 3 * Cc, seed=61)
+    out = torch.zeros(B * Fr * HW, Cc, device="cuda", dtype=torch.half)
+    check(lib().hv_op_temporal_attention(ptr(qkv), ptr(out), i64(B), i64(Fr), i64(HW), i32(heads), i32(d), stream()))
+    q, k, v = qkv.float().reshape(B, Fr, HW, 3, heads, d).permute(3, 0, 2, 4, 1, 5)  # (b, hw, h, f, d)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 3, 1, 2, 4).reshape(B * Fr * HW, Cc)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel(out, ref) < 2e-3
+
+
 def attention_case(NF, L, heads, d, Lb=0, Fr=1, nf_nobank=0, seed=70):
     dpad = (d + 15) // 16 * 16
     q = dev(NF * L, heads, d, seed=seed)
