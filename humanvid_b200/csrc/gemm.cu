@@ -187,10 +187,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb)
           tma_load_2d(smem + kb * C::kBTileBytes, &map_b, bar_bpanel, kb * BLOCK_K, (blockIdx.x % n_tiles) * BLOCK_N);
       }
+      // Optional L2 prefetch of the A stream, p.pf_dist k-blocks ahead of the loads (HV_GEMM_PF, default off).  Measured
+      // NEGATIVE: +17 % time on the K = 320 linears, +35 % on the convs -- these kernels are bound by the request rate of the
+      // SM's TMA unit (~0.45 box rows per clock, 128 B each = the 58 B/clk fill rate), and every prefetch is another request.
+      int pf_tile = blockIdx.x, pf_kb = 0;
+      auto pf_step = [&]() {
+        if (pf_tile >= num_tiles) return;
+        const TileCoord pc = tile_coord(p, pf_tile / n_tiles, TILE_M);
+        if (p.a_mode == A_LINEAR) {
+          if (p.k_split == 0 || pf_kb < p.k_split) tma_prefetch_2d(&map_a0, pf_kb * BLOCK_K, pc.m0);   // the box spans all TILE_M rows
+          else tma_prefetch_2d(&map_a1, (pf_kb - p.k_split) * BLOCK_K, pc.m0);
+        } else if (p.a_mode == A_CONV3X3) {
+          const int tap = pf_kb / p.cin_blocks, cb = pf_kb - tap * p.cin_blocks;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          tma_prefetch_4d(&map_a0, cb * BLOCK_K, pc.x0 + dx - 1, pc.y0 + dy - 1, pc.n0);
+        }
+        if (++pf_kb == nkb) { pf_kb = 0; pf_tile += gridDim.x; }
+      };
+      const bool do_pf = p.pf_dist > 0 && p.a_mode != A_CONV3X3_S2;
+      if (do_pf)
+        for (int i = 0; i < p.pf_dist; ++i) pf_step();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const TileCoord tc = tile_coord(p, m_blk, TILE_M);
         for (int kb = 0; kb < nkb; ++kb) {
+          if (do_pf) pf_step();
           mbar_wait(&bar_empty[stage], phase ^ 1);
           uint8_t* sa = ring + stage * kRingStageBytes;
           uint8_t* sb = sa + C::kATileBytes;
@@ -662,9 +683,12 @@ static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, cons
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p,
+cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p_in,
                         const GemmEpilogue& e_in, int block_n, int num_sms, cudaStream_t stream, int m_sub, const CUtensorMap* io_out,
                         const CUtensorMap* io_res) {
+  static const int pf_env = [] { const char* v = getenv("HV_GEMM_PF"); return v ? atoi(v) : 0; }();  // experiment, off: the extra TMA requests cost more than the latency they hide
+  GemmProblem p = p_in;
+  p.pf_dist = pf_env;
   GemmEpilogue e = e_in;
   e.tma_io = (io_out != nullptr && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && (e.residual == nullptr || e.geglu || io_res != nullptr)) ? 1 : 0;
   const CUtensorMap& mo = e.tma_io ? *io_out : a0;

@@ -31,6 +31,7 @@ struct GemmProblem {
   int M = 0, N = 0;                // logical rows / packed columns of D
   int num_k_blocks = 0;            // ceil(K / 64)
   int bst_stages = 0;              // set by launch_gemm: A-ring depth of the B-stationary variant
+  int pf_dist = 0;                 // set by launch_gemm: the producer prefetches A boxes this many k-blocks ahead into L2
   int a_mode = A_LINEAR;
   int k_split = 0;                 // A_LINEAR: k-blocks taken from tensor map a0 (rest from a1); 0 = all from a0
   int cin_blocks = 0;              // conv: 64-channel blocks per tap
