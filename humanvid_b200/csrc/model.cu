@@ -107,6 +107,7 @@ struct SpatialW {
   Lin v2, out2;  // cross-attention collapse: to_v (C x xdim), to_out
   Lin ff1, ff2;  // ff1 geglu-packed
   int C = 0, heads = 0, d = 0, dpad = 0;
+  int reader_idx = -1;
   // reference bank (B_ref, L, C)
   __half* bank = nullptr;
   int64_t bank_B = 0, bank_L = 0;
@@ -205,6 +206,7 @@ struct hv_model {
   Norm norm_out;
   Conv3 conv_out;
   std::vector<SpatialW*> readers;  // reference-bank order
+  __half* const* bank_out = nullptr;  // writer forward: reader-order destinations of every block's LayerNorm-1 output (the "bank")
   // ---- PoseGuider
   ConvDirect pg_in;
   std::vector<Conv3> pg_convs;  // blocks.0..5, conv_out
@@ -425,14 +427,17 @@ struct hv_model {
       if (u.has_up) u.up = conv3(p + ".upsamplers.0.conv", c, c);
       prev = c;
     }
-    norm_out = norm("conv_norm_out", ch[0], 1e-5f);
-    conv_out = conv3("conv_out", cfg.out_channels, ch[0]);
+    if (cfg.kind == HV_KIND_UNET3D) {   // the reference ("writer") 2-D UNet has its post-process removed (unet_2d_condition.py:1295-1299)
+      norm_out = norm("conv_norm_out", ch[0], 1e-5f);
+      conv_out = conv3("conv_out", cfg.out_channels, ch[0]);
+    }
     // reader order: DFS(down_blocks, up_blocks, mid_block), stable sort by descending width
     readers.clear();
     for (auto& d : down) for (auto& a : d.attn) readers.push_back(&a);
     for (auto& u : up) for (auto& a : u.attn) readers.push_back(&a);
     for (auto& a : mid.attn) readers.push_back(&a);
     std::stable_sort(readers.begin(), readers.end(), [](const SpatialW* x, const SpatialW* y) { return x->C > y->C; });
+    for (size_t i = 0; i < readers.size(); ++i) readers[i]->reader_idx = static_cast<int>(i);
   }
 
   void build_pose_guider() {
@@ -612,7 +617,12 @@ struct hv_model {
         Timed tm(this, CAT_GEMM, 2.0 * tokens * C * C, "gemm_vt", vrows, tokens, C);
         ckop(op_gemm_batched_b(w.wv.p, C, n1.p, C, vt, ldvt, vrows, x.NF, L, Lp, C, w.vones, st), "V^T gemm");
       }
-      const bool use_bank = w.bank != nullptr;
+      // write hook (mutual_self_attention.py:137-146): the bank IS LayerNorm-1's output; attention then runs on itself only
+      if (bank_out != nullptr && !ar.dry) {
+        launches += 1;
+        ck(cudaMemcpyAsync(bank_out[w.reader_idx], n1.p, static_cast<size_t>(tokens) * C * 2, cudaMemcpyDeviceToDevice, st), "bank write");
+      }
+      const bool use_bank = w.bank != nullptr && bank_out == nullptr;
       __half *kb = nullptr, *vbt = nullptr;
       int64_t ldvbt = 0, Lbp = 0;
       if (use_bank) {
@@ -779,6 +789,10 @@ struct hv_model {
         h = op_conv3(big, u.up, 1, nullptr, 1, HV_ACT_NONE, nullptr);
       }
     }
+    if (cfg.kind == HV_KIND_UNET2D_REF) {   // no post-process: the forward's value is the last up block's output (B, C0, h, w)
+      if (outp != nullptr && !ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(h.p, h.C, outp, B, ch[0], F, H, W, st), "hidden layout"); }
+      return;
+    }
     Tens hn = op_gn(h, nullptr, norm_out, true);
     Tens y = op_conv3(hn, conv_out, 1, nullptr, 1, HV_ACT_NONE, nullptr);
     if (!ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(y.p, y.C, outp, B, cfg.out_channels, F, H, W, st), "output layout"); }
@@ -869,7 +883,8 @@ int hv_create(const hv_config* cfg, hv_handle* out) {
     m = new hv_model();
     m->cfg = *cfg;
     m->sms = sms;
-    if (cfg->kind < 0 || cfg->kind > 2) fail(HV_ERR_INVALID, "unknown kind %d", cfg->kind);
+    if (cfg->kind < 0 || cfg->kind > 3) fail(HV_ERR_INVALID, "unknown kind %d", cfg->kind);
+    if (cfg->kind == HV_KIND_UNET2D_REF && cfg->use_motion_module) fail(HV_ERR_INVALID, "the reference (writer) UNet has no motion modules");
     *out = m;
     return HV_OK;
   } catch (const Err& e) {
@@ -958,7 +973,7 @@ int hv_finalize(hv_handle h, hv_stream_t stream) {
   HV_GUARD(h, {
     if (h->finalized) return HV_OK;
     h->st = static_cast<cudaStream_t>(stream);
-    if (h->cfg.kind == HV_KIND_UNET3D) h->build_unet();
+    if (h->cfg.kind == HV_KIND_UNET3D || h->cfg.kind == HV_KIND_UNET2D_REF) h->build_unet();
     else if (h->cfg.kind == HV_KIND_POSE_GUIDER) h->build_pose_guider();
     else h->build_camera();
     h->finalized = true;
@@ -996,9 +1011,9 @@ int hv_clear_ref_banks(hv_handle h) {
 
 static size_t measure(hv_model* h, int B, int F, int H, int W) {
   h->begin(nullptr, 0, true, nullptr);
-  if (h->cfg.kind == HV_KIND_UNET3D) {
+  if (h->cfg.kind == HV_KIND_UNET3D || h->cfg.kind == HV_KIND_UNET2D_REF) {
     static __half dummy;
-    h->unet_forward(&dummy, 0, &dummy, &dummy, &dummy, B, F, H, W, HV_FLAG_CFG);
+    h->unet_forward(&dummy, 0, &dummy, h->cfg.kind == HV_KIND_UNET3D ? &dummy : nullptr, &dummy, B, F, H, W, HV_FLAG_CFG);
   } else if (h->cfg.kind == HV_KIND_POSE_GUIDER) {
     h->pose_guider_forward(nullptr, nullptr, B, F, H, W);
   } else {
@@ -1028,6 +1043,30 @@ int hv_unet3d_forward(hv_handle h, const void* sample, int64_t timestep, const v
     h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
     h->unet_forward(static_cast<const __half*>(sample), timestep, static_cast<const __half*>(ehs), static_cast<const __half*>(pose),
                     static_cast<__half*>(out), B, F, height, width, flags);
+  });
+}
+
+int hv_unet2d_reference_forward(hv_handle h, const void* sample, int64_t timestep, const void* ehs, void* hidden_out, void* const* bank_out,
+                                int32_t n_banks, int32_t B, int32_t height, int32_t width, void* workspace, size_t ws_bytes, hv_stream_t stream) {
+  if (!h || !sample || !ehs || !bank_out) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized || h->cfg.kind != HV_KIND_UNET2D_REF) fail(HV_ERR_STATE, "handle is not a finalized reference (writer) UNet2D");
+    if (n_banks != static_cast<int>(h->readers.size())) fail(HV_ERR_INVALID, "expected %d bank destinations, got %d", (int)h->readers.size(), n_banks);
+    for (int i = 0; i < n_banks; ++i)
+      if (bank_out[i] == nullptr) fail(HV_ERR_INVALID, "bank destination %d is NULL", i);
+    const size_t need = measure(h, B, 1, height, width);
+    size_t have = 0;
+    void* ws = get_ws(h, workspace, ws_bytes, need, &have);
+    h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
+    h->bank_out = reinterpret_cast<__half* const*>(bank_out);
+    try {
+      h->unet_forward(static_cast<const __half*>(sample), timestep, static_cast<const __half*>(ehs), nullptr, static_cast<__half*>(hidden_out), B, 1,
+                      height, width, 0);
+    } catch (...) {
+      h->bank_out = nullptr;
+      throw;
+    }
+    h->bank_out = nullptr;
   });
 }
 

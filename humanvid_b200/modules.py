@@ -7,6 +7,8 @@
   * ``UNet3DConditionModel.forward``  <->  src/models/unet_3d.py:397-577
   * ``PoseGuider.forward``            <->  src/models/pose_guider.py:51-61
   * ``CameraPoseEncoder.forward``     <->  src/cameractrl/pose_adaptor.py:232-248
+  * ``UNet2DConditionModel.forward``  <->  src/models/unet_2d_condition.py:872-1308 (the reference / "writer" UNet, whose
+    LayerNorm-1 outputs become the denoising UNet's K/V banks)
 
 The ``nn.Module`` tree below only *holds parameters* under the reference's names (torch is plumbing: device memory,
 ``load_state_dict``, ``.to()``); none of its sub-modules' ``forward`` is ever executed.  All arithmetic happens in
@@ -78,12 +80,16 @@ class TemporalBasicTransformerBlock(_Shell):
         self.bank: List[torch.Tensor] = []
 
 
+class BasicTransformerBlock(TemporalBasicTransformerBlock):
+    """Writer-side block of the 2-D reference UNet (src/models/attention.py BasicTransformerBlock): same parameters."""
+
+
 class _Transformer3D(_Shell):
-    def __init__(self, ch, cross_attention_dim, groups):
+    def __init__(self, ch, cross_attention_dim, groups, block_cls=None):
         super().__init__()
         self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
         self.proj_in = _conv(ch, ch, 1)
-        self.transformer_blocks = nn.ModuleList([TemporalBasicTransformerBlock(ch, cross_attention_dim)])
+        self.transformer_blocks = nn.ModuleList([(block_cls or TemporalBasicTransformerBlock)(ch, cross_attention_dim)])
         self.proj_out = _conv(ch, ch, 1)
 
 
@@ -151,12 +157,13 @@ class _Sampler(_Shell):
 
 
 class _Block(_Shell):
-    def __init__(self, res_io, ch, attn, motion, xdim, temb, groups, max_len, sampler=None):
+    def __init__(self, res_io, ch, attn, motion, xdim, temb, groups, max_len, sampler=None, block_cls=None):
         super().__init__()
         if attn:
-            self.attentions = nn.ModuleList([_Transformer3D(ch, xdim, groups) for _ in range(attn)])
+            self.attentions = nn.ModuleList([_Transformer3D(ch, xdim, groups, block_cls) for _ in range(attn)])
         self.resnets = nn.ModuleList([_Resnet(i, o, temb, groups) for i, o in res_io])
-        self.motion_modules = nn.ModuleList([_MotionModule(ch, max_len, groups) if motion else None for _ in range(max(attn, len(res_io)) if sampler != "mid" else 1)])
+        if block_cls is None:   # the 2-D reference UNet's blocks (block_cls given) have no motion_modules attribute
+            self.motion_modules = nn.ModuleList([_MotionModule(ch, max_len, groups) if motion else None for _ in range(max(attn, len(res_io)) if sampler != "mid" else 1)])
         if sampler == "down":
             self.downsamplers = nn.ModuleList([_Sampler(ch, 2)])
         elif sampler == "up":
@@ -509,6 +516,169 @@ class UNet3DConditionModel(_NativeNet):
         model.load_state_dict(state, strict=False)
         return model
 
+# --------------------------------------------------------------------------------------------- reference ("writer") UNet
+@dataclass
+class UNet2DConditionOutput:
+    sample: torch.Tensor
+
+
+class UNet2DConditionModel(_NativeNet):
+    """Drop-in for the reference ("writer") UNet, src/models/unet_2d_condition.py (SD1.5 layout), inference only.
+
+    ``forward(sample (b,4,h,w), timestep, encoder_hidden_states (b,1,dim))`` returns what the reference returns -- the last
+    up block's output (b, 320, h, w); the post-process is removed there (unet_2d_condition.py:1295-1299).  Under
+    ``ReferenceAttentionControl(self, mode="write", fusion_blocks="full")`` every transformer block's LayerNorm-1 output
+    is left in ``block.bank`` (mutual_self_attention.py:137-146), ready for ``reader.update(writer)``.  The native forward
+    (``hv_unet2d_reference_forward``) is the denoising UNet's own kernels at one frame without motion modules.
+    """
+
+    _kind = 3
+
+    def __init__(
+        self,
+        sample_size: Optional[int] = None,
+        in_channels: int = 4,
+        out_channels: int = 4,
+        center_input_sample: bool = False,
+        flip_sin_to_cos: bool = True,
+        freq_shift: int = 0,
+        down_block_types: Tuple[str, ...] = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+        mid_block_type: Optional[str] = "UNetMidBlock2DCrossAttn",
+        up_block_types: Tuple[str, ...] = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+        only_cross_attention=False,
+        block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280),
+        layers_per_block=2,
+        downsample_padding: int = 1,
+        mid_block_scale_factor: float = 1,
+        act_fn: str = "silu",
+        norm_num_groups: Optional[int] = 32,
+        norm_eps: float = 1e-5,
+        cross_attention_dim=1280,
+        attention_head_dim=8,
+        dual_cross_attention: bool = False,
+        use_linear_projection: bool = False,
+        class_embed_type: Optional[str] = None,
+        num_class_embeds: Optional[int] = None,
+        upcast_attention: bool = False,
+        resnet_time_scale_shift: str = "default",
+        **unused,
+    ):
+        super().__init__()
+        unsupported = []
+        if tuple(down_block_types) != ("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",) or tuple(up_block_types) != ("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3 \
+                or mid_block_type != "UNetMidBlock2DCrossAttn":
+            unsupported.append("block types other than the SD1.5 layout")
+        if layers_per_block != 2 or len(block_out_channels) != 4:
+            unsupported.append("layers_per_block != 2 / depth != 4")
+        if center_input_sample or not flip_sin_to_cos or freq_shift != 0 or use_linear_projection or dual_cross_attention or only_cross_attention:
+            unsupported.append("center_input_sample / flip_sin_to_cos=False / freq_shift / use_linear_projection / dual / only_cross_attention")
+        if class_embed_type is not None or num_class_embeds is not None or resnet_time_scale_shift != "default" or act_fn not in ("silu", "swish") \
+                or mid_block_scale_factor != 1 or not isinstance(attention_head_dim, int) or norm_num_groups is None:
+            unsupported.append("class embeddings / non-default resnet, activation or norm options")
+        if unsupported:
+            raise NotImplementedError("humanvid_b200.UNet2DConditionModel implements the SD1.5 reference-UNet layout only; unsupported: " + "; ".join(unsupported))
+        self.config = SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("self", "unsupported", "unused", "__class__")})
+        self.sample_size = sample_size
+        self.in_channels = in_channels
+        ch = list(block_out_channels)
+        heads, xdim, g = attention_head_dim, cross_attention_dim, norm_num_groups
+        temb = ch[0] * 4
+        self._heads = heads
+        self.conv_in = _conv(in_channels, ch[0], 3, padding=1)
+        self.time_embedding = _TimestepEmbedding(ch[0], temb)
+        self.down_blocks = nn.ModuleList([])
+        self.up_blocks = nn.ModuleList([])
+        prev = ch[0]
+        for i, c in enumerate(ch):
+            last = i == 3
+            self.down_blocks.append(_Block([(prev, c), (c, c)], c, 0 if last else 2, False, xdim, temb, g, 0, None if last else "down", block_cls=BasicTransformerBlock))
+            prev = c
+        self.mid_block = _Block([(ch[3], ch[3]), (ch[3], ch[3])], ch[3], 1, False, xdim, temb, g, 0, "mid", block_cls=BasicTransformerBlock)
+        rev = ch[::-1]
+        prev = rev[0]
+        for i, c in enumerate(rev):
+            cin = rev[min(i + 1, 3)]
+            io = [((prev if j == 0 else c) + (cin if j == 2 else c), c) for j in range(3)]
+            self.up_blocks.append(_Block(io, c, 0 if i == 0 else 3, False, xdim, temb, g, 0, "up" if i < 3 else None, block_cls=BasicTransformerBlock))
+            prev = c
+        self._ref_write = False
+
+    # ---- banks (ReferenceAttentionControl, write side) ---------------------------------------------------------
+    def writer_blocks(self) -> List[Tuple[BasicTransformerBlock, int]]:
+        """(block, level) in ``update()`` order: DFS(down_blocks, up_blocks, mid_block), stable sort by descending width."""
+        out = []
+        for i, b in enumerate(self.down_blocks):
+            for a in getattr(b, "attentions", []):
+                out.append((a.transformer_blocks[0], i))
+        for i, b in enumerate(self.up_blocks):
+            for a in getattr(b, "attentions", []):
+                out.append((a.transformer_blocks[0], 3 - i))
+        out.append((self.mid_block.attentions[0].transformer_blocks[0], 3))
+        return sorted(out, key=lambda t: -t[0].norm1.normalized_shape[0])
+
+    def _hv_config(self):
+        c = self.config
+        cfg = HvConfig()
+        cfg.kind = 3
+        cfg.in_channels, cfg.out_channels = c.in_channels, c.out_channels
+        cfg.block_out_channels = (C.c_int32 * 4)(*c.block_out_channels)
+        cfg.heads, cfg.cross_attention_dim, cfg.norm_groups = c.attention_head_dim, c.cross_attention_dim, c.norm_num_groups
+        cfg.use_motion_module, cfg.motion_max_len = 0, 0
+        return cfg
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states: torch.Tensor,
+                class_labels: Optional[torch.Tensor] = None, timestep_cond=None, attention_mask=None, cross_attention_kwargs=None,
+                added_cond_kwargs=None, down_block_additional_residuals=None, mid_block_additional_residual=None,
+                down_intrablock_additional_residuals=None, encoder_attention_mask=None, return_dict: bool = True):
+        if any(v is not None for v in (class_labels, timestep_cond, attention_mask, cross_attention_kwargs, added_cond_kwargs, down_block_additional_residuals,
+                                       mid_block_additional_residual, down_intrablock_additional_residuals, encoder_attention_mask)):
+            raise NotImplementedError("only (sample, timestep, encoder_hidden_states) are part of the CamAnimate reference-UNet call")
+        if sample.dim() != 4:
+            raise ValueError(f"Expected sample to have ndim=4 (b c h w), got {sample.dim()}")
+        B, Cc, H, W = sample.shape
+        if Cc != self.in_channels:
+            raise ValueError(f"sample has {Cc} channels, model expects {self.in_channels}")
+        h = self._sync_native()
+        x = self._as_half(sample, "sample")
+        ehs = self._as_half(encoder_hidden_states, "encoder_hidden_states")
+        if ehs.shape[0] != B or ehs.shape[1] != 1:
+            raise ValueError(f"encoder_hidden_states must be (batch, 1, dim) with batch {B}; got {tuple(ehs.shape)}")
+        t = int(timestep.reshape(-1)[0].item()) if torch.is_tensor(timestep) else int(timestep)
+        blocks = self.writer_blocks()
+        banks = [torch.empty((B, (H >> lvl) * (W >> lvl), blk.norm1.normalized_shape[0]), device=x.device, dtype=torch.float16) for blk, lvl in blocks]
+        hidden = torch.empty((B, self.config.block_out_channels[0], H, W), device=x.device, dtype=torch.float16)
+        ptrs = (C.c_void_p * len(banks))(*[b.data_ptr() for b in banks])
+        N.check(N.lib().hv_unet2d_reference_forward(h, N.ptr(x), N.i64(t), N.ptr(ehs), N.ptr(hidden), ptrs, N.i32(len(banks)), N.i32(B), N.i32(H), N.i32(W),
+                                                    None, C.c_size_t(0), N.stream()), h)
+        if self._ref_write:
+            for (blk, _), bank in zip(blocks, banks):
+                blk.bank.append(bank)
+        hidden = hidden.to(sample.dtype) if sample.dtype != torch.float16 else hidden
+        if not return_dict:
+            return (hidden,)
+        return UNet2DConditionOutput(sample=hidden)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, **kwargs):
+        """diffusers-style loader (scripts/pose2vid.py:72-75): ``<path>/<subfolder>/config.json`` + ``diffusion_pytorch_model.{safetensors,bin}``."""
+        path = os.path.join(str(pretrained_model_path), subfolder) if subfolder is not None else str(pretrained_model_path)
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        import inspect
+
+        allowed = set(inspect.signature(cls.__init__).parameters) - {"self", "unused"}
+        model = cls(**{k: v for k, v in cfg.items() if k in allowed})
+        st_path = os.path.join(path, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.torch import load_file
+
+            state = load_file(st_path, device="cpu")
+        else:
+            state = torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu", weights_only=True)
+        model.load_state_dict(state, strict=False)   # SD checkpoints also carry conv_norm_out / conv_out, unused by the reference UNet
+        return model
+
 
 # --------------------------------------------------------------------------------------------- PoseGuider
 class PoseGuider(_NativeNet):
@@ -615,32 +785,43 @@ class CameraPoseEncoder(_NativeNet):
 
 # --------------------------------------------------------------------------------------------- ReferenceAttentionControl (reader)
 class ReferenceAttentionControl:
-    """Reader side of src/models/mutual_self_attention.py for a native UNet3DConditionModel.
+    """src/models/mutual_self_attention.py for the native UNets: same constructor keywords / ``update(writer)`` / ``clear()``.
 
-    Same constructor keywords / ``update(writer)`` / ``clear()``.  ``writer`` is the reference's own
-    ReferenceAttentionControl(mode="write") around its PyTorch 2-D UNet (or anything exposing ``.unet`` whose
-    transformer blocks carry ``norm1`` and a ``bank`` list): banks are matched in the same sorted order.
-    The reference implements the read path by monkey-patching ``forward`` of every block and concatenating the bank;
-    here ``update`` hands the banks to the native attention kernel, which reads them as a second key/value segment.
+    ``mode="read"`` wraps a native ``UNet3DConditionModel`` (the denoising UNet): ``update`` hands the banks to the native
+    attention kernel, which reads them as a second key/value segment (the reference monkey-patches every block's forward
+    and concatenates).  ``mode="write"`` wraps a native ``UNet2DConditionModel`` (the reference UNet): its next forward
+    leaves every block's LayerNorm-1 output in ``block.bank``.  ``update`` also accepts the reference's own PyTorch writer
+    (anything exposing ``.unet`` whose transformer blocks carry ``norm1`` and a ``bank`` list); banks are matched in the
+    same sorted order (mutual_self_attention.py:302-339).
     """
 
     def __init__(self, unet, mode="read", do_classifier_free_guidance=False, attention_auto_machine_weight=float("inf"),
                  gn_auto_machine_weight=1.0, style_fidelity=1.0, reference_attn=True, reference_adain=False, fusion_blocks="midup",
                  batch_size=1):
-        if mode != "read":
-            raise NotImplementedError("the native UNet is the reader; use the reference's ReferenceAttentionControl for mode='write'")
+        if mode not in ("read", "write"):
+            raise ValueError("mode must be 'read' or 'write'")
         if fusion_blocks != "full" or reference_adain or not reference_attn:
             raise NotImplementedError("only fusion_blocks='full', reference_attn=True (what pipeline_pose2vid_long.py uses)")
-        if not isinstance(unet, UNet3DConditionModel):
-            raise TypeError("unet must be a humanvid_b200.UNet3DConditionModel")
         self.unet = unet
-        unet._ref_cfg = bool(do_classifier_free_guidance)
-        for m in unet.reader_blocks():
-            m.bank = []
+        self.mode = mode
+        if mode == "read":
+            if not isinstance(unet, UNet3DConditionModel):
+                raise TypeError("mode='read' needs a humanvid_b200.UNet3DConditionModel")
+            unet._ref_cfg = bool(do_classifier_free_guidance)
+            for m in unet.reader_blocks():
+                m.bank = []
+        else:
+            if not isinstance(unet, UNet2DConditionModel):
+                raise TypeError("mode='write' needs a humanvid_b200.UNet2DConditionModel (or use the reference's own writer around its PyTorch UNet)")
+            unet._ref_write = True
+            for m, _ in unet.writer_blocks():
+                m.bank = []
 
     @staticmethod
     def _writer_blocks(writer):
         root = writer.unet if hasattr(writer, "unet") else writer
+        if isinstance(root, UNet2DConditionModel):
+            return [m for m, _ in root.writer_blocks()]
 
         def dfs(m):
             out = [m]
@@ -652,11 +833,17 @@ class ReferenceAttentionControl:
         return sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
 
     def update(self, writer, dtype=torch.float16):
+        if self.mode != "read":
+            raise RuntimeError("update() is called on the reader")
         readers = self.unet.reader_blocks()
         writers = self._writer_blocks(writer)
         for r, w in zip(readers, writers):
             r.bank = [v.clone().to(dtype) for v in w.bank]
 
     def clear(self):
-        for r in self.unet.reader_blocks():
-            r.bank.clear()
+        if self.mode == "read":
+            for r in self.unet.reader_blocks():
+                r.bank.clear()
+        else:
+            for m, _ in self.unet.writer_blocks():
+                m.bank.clear()

@@ -149,6 +149,10 @@ class Pose2VideoPipeline(_PipelineBase):
         writer_cls, reader_cls = self.reference_control_cls or (None, None)
         if reader_cls is None:
             from .modules import ReferenceAttentionControl as reader_cls
+        if writer_cls is None and self.reference_unet is not None:
+            from .modules import ReferenceAttentionControl, UNet2DConditionModel
+            if isinstance(self.reference_unet, UNet2DConditionModel):   # native reference UNet: the native control writes its banks
+                writer_cls = ReferenceAttentionControl
         writer = writer_cls(self.reference_unet, do_classifier_free_guidance=cfg_on, mode="write", batch_size=batch_size, fusion_blocks="full") \
             if writer_cls is not None else None
         reader = reader_cls(self.denoising_unet, do_classifier_free_guidance=cfg_on, mode="read", batch_size=batch_size, fusion_blocks="full")
@@ -232,6 +236,10 @@ class Pose2ImagePipeline(_PipelineBase):
         writer_cls, reader_cls = self.reference_control_cls or (None, None)
         if reader_cls is None:
             from .modules import ReferenceAttentionControl as reader_cls
+        if writer_cls is None and self.reference_unet is not None:
+            from .modules import ReferenceAttentionControl, UNet2DConditionModel
+            if isinstance(self.reference_unet, UNet2DConditionModel):   # native reference UNet: the native control writes its banks
+                writer_cls = ReferenceAttentionControl
         writer = writer_cls(self.reference_unet, do_classifier_free_guidance=cfg_on, mode="write", batch_size=1, fusion_blocks="full") \
             if writer_cls is not None else None
         reader = reader_cls(self.denoising_unet, do_classifier_free_guidance=cfg_on, mode="read", batch_size=1, fusion_blocks="full")

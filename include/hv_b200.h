@@ -8,6 +8,9 @@
  *   HV_KIND_CAMERA_ENCODER CameraPoseEncoder.forward     src/cameractrl/pose_adaptor.py:232-248
  *   hv_set_ref_bank / hv_clear_ref_banks                 ReferenceAttentionControl.update / .clear
  *                                                        src/models/mutual_self_attention.py:302-363
+ *   HV_KIND_UNET2D_REF    UNet2DConditionModel.forward in "write" mode (the reference / "writer" UNet, once per clip)
+ *                                                        src/models/unet_2d_condition.py:872-1308 (post-process removed
+ *                                                        :1295-1299), write hook mutual_self_attention.py:137-146
  *
  * Contract: all tensor arguments are caller-owned CUDA device pointers (torch allocations), contiguous, fp16 unless
  * stated, in the reference's own layouts ((B,C,F,H,W) etc.).  The library owns only its packed weights, reference
@@ -27,7 +30,7 @@ extern "C" {
 
 typedef struct hv_model* hv_handle;
 
-enum hv_kind { HV_KIND_UNET3D = 0, HV_KIND_POSE_GUIDER = 1, HV_KIND_CAMERA_ENCODER = 2 };
+enum hv_kind { HV_KIND_UNET3D = 0, HV_KIND_POSE_GUIDER = 1, HV_KIND_CAMERA_ENCODER = 2, HV_KIND_UNET2D_REF = 3 };
 enum hv_dtype { HV_F16 = 0, HV_F32 = 1 };
 enum hv_forward_flags {
   HV_FLAG_CFG = 1 /* batch = [uncond half ; cond half]: the first half ignores the reference banks
@@ -84,6 +87,14 @@ size_t hv_workspace_bytes(hv_handle h, int32_t B, int32_t F, int32_t height, int
 int hv_unet3d_forward(hv_handle h, const void* sample, int64_t timestep, const void* encoder_hidden_states, const void* pose_cond_fea,
                       void* out, int32_t B, int32_t F, int32_t height, int32_t width, uint32_t flags, void* workspace,
                       size_t ws_bytes, hv_stream_t stream);
+/* Reference ("writer") UNet, kind HV_KIND_UNET2D_REF (hv_config as for the UNet3D with use_motion_module = 0; no
+ * conv_norm_out / conv_out weights).  sample (B,4,h,w), encoder_hidden_states (B,1,cross_attention_dim);
+ * bank_out[i] (i in reader order, see hv_num_ref_blocks / hv_ref_block_dim) receives block i's LayerNorm-1 output
+ * (B, h_i*w_i, C_i) fp16 -- exactly what hv_set_ref_bank of the denoising UNet takes; hidden_out (B,C0,h,w) or NULL is
+ * the forward's return value (the last up block's output). */
+int hv_unet2d_reference_forward(hv_handle h, const void* sample, int64_t timestep, const void* encoder_hidden_states, void* hidden_out,
+                                void* const* bank_out, int32_t n_banks, int32_t B, int32_t height, int32_t width, void* workspace,
+                                size_t ws_bytes, hv_stream_t stream);
 /* conditioning (B,3,F,H,W) -> out (B,320,F,H/8,W/8) */
 int hv_pose_guider_forward(hv_handle h, const void* conditioning, void* out, int32_t B, int32_t F, int32_t H, int32_t W,
                            void* workspace, size_t ws_bytes, hv_stream_t stream);

@@ -209,10 +209,13 @@ class TemporalBasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim)
         self.bank: List[torch.Tensor] = []
         self.ref_read = False
+        self.ref_write = False   # write hook (mutual_self_attention.py:137-146): bank.append(norm_hidden_states.clone())
         self.ref_cfg = True
 
     def forward(self, h, encoder_hidden_states=None, video_length=None, **_):
         n = self.norm1(h)
+        if self.ref_write:
+            self.bank.append(n.clone())
         if self.ref_read:
             feats = [d.unsqueeze(1).repeat(1, video_length, 1, 1).flatten(0, 1) for d in self.bank]
             kv = torch.cat([n] + feats, dim=1)
@@ -549,6 +552,53 @@ class UNet3DConditionModel(nn.Module):
             h = blk(h, res, emb, encoder_hidden_states)
         h = self.conv_out(F.silu(self.conv_norm_out(h)))
         return (h,)
+
+
+class UNet2DConditionModel(UNet3DConditionModel):
+    """The reference ("writer") UNet: SD1.5 2-D UNet, src/models/unet_2d_condition.py:872-1308 with its blocks
+    (unet_2d_blocks.py: CrossAttnDownBlock2D :409-505, DownBlock2D :508-570, UNetMidBlock2DCrossAttn :573-670,
+    CrossAttnUpBlock2D :854-975, UpBlock2D :978-1074) and Transformer2DModel (transformer_2d.py:213-396).
+
+    Arithmetically it is the 3-D UNet above at one frame without motion modules and without pose residual: every
+    module is the 2-D original applied per frame, state-dict keys are identical.  Two differences of the forward:
+    the post-process (conv_norm_out / SiLU / conv_out) is REMOVED (unet_2d_condition.py:645-652 no modules, :1295-1299 no
+    call) -- the value is the last up block's output -- and, under ReferenceAttentionControl(mode="write")
+    (mutual_self_attention.py:137-146), every BasicTransformerBlock appends its LayerNorm-1 output to ``bank``.
+    """
+
+    def __init__(self, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), heads=8, cross_attention_dim=768):
+        super().__init__(in_channels, out_channels, block_out_channels, heads, cross_attention_dim, use_motion_module=False,
+                         use_inflated_groupnorm=False)
+        del self.conv_norm_out, self.conv_out   # unet_2d_condition.py:645-652: conv_norm_out = None, conv_out commented out
+
+    def forward(self, sample, timestep, encoder_hidden_states, return_dict=False, **_):
+        x = sample.unsqueeze(2)                                         # (b, c, 1, h, w)
+        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
+        t = t.reshape(-1).to(sample.device).expand(sample.shape[0])
+        emb = self.time_embedding(timestep_sincos(t, self.conv_in.out_channels).to(self.dtype))
+        h = self.conv_in(x)
+        skips = (h,)
+        for blk in self.down_blocks:
+            h, outs = blk(h, emb, encoder_hidden_states)
+            skips += outs
+        h = self.mid_block(h, emb, encoder_hidden_states)
+        for blk in self.up_blocks:
+            n = len(blk.resnets)
+            res, skips = skips[-n:], skips[:-n]
+            h = blk(h, res, emb, encoder_hidden_states)
+        return (h.squeeze(2),)
+
+
+def set_reference_write(unet: nn.Module, on: bool = True):
+    """ReferenceAttentionControl(unet, mode="write", fusion_blocks="full"): clear the banks and arm the write hook."""
+    for b in torch_dfs(unet):
+        if isinstance(b, TemporalBasicTransformerBlock):
+            b.bank, b.ref_write, b.ref_read = [], on, False
+
+
+def written_banks(unet: nn.Module) -> List[torch.Tensor]:
+    """The banks in ``ReferenceAttentionControl.update`` order (descending width, stable) -- one (B, L, C) tensor per block."""
+    return [b.bank[0] for b in reader_blocks(unet)]
 
 
 # ----------------------------------------------------------------------------------------

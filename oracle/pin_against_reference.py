@@ -185,6 +185,90 @@ class DTimestepEmbedding(nn.Module):
         return self.linear_2(self.act(self.linear_1(x)))
 
 
+# ---- diffusers 0.24.0 2-D primitives the reference ("writer") UNet imports: resnet.py ResnetBlock2D / Downsample2D /
+# Upsample2D and the LoRA-compatible layers (plain layers that ignore the lora ``scale`` argument when no LoRA is loaded)
+class LoRACompatibleConv(nn.Conv2d):
+    def forward(self, x, scale=1.0):
+        return super().forward(x)
+
+
+class LoRACompatibleLinear(nn.Linear):
+    def forward(self, x, scale=1.0):
+        return super().forward(x)
+
+
+class DResnetBlock2D(nn.Module):
+    def __init__(self, *, in_channels, out_channels=None, conv_shortcut=False, dropout=0.0, temb_channels=512, groups=32, groups_out=None,
+                 pre_norm=True, eps=1e-6, non_linearity="swish", skip_time_act=False, time_embedding_norm="default", kernel=None,
+                 output_scale_factor=1.0, use_in_shortcut=None, up=False, down=False, **_):
+        super().__init__()
+        assert time_embedding_norm == "default" and not up and not down and kernel is None
+        out_channels = out_channels or in_channels
+        self.output_scale_factor = output_scale_factor
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = LoRACompatibleConv(in_channels, out_channels, 3, stride=1, padding=1)
+        self.time_emb_proj = LoRACompatibleLinear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups_out or groups, out_channels, eps=eps, affine=True)
+        self.dropout = nn.Dropout(dropout)
+        self.conv2 = LoRACompatibleConv(out_channels, out_channels, 3, stride=1, padding=1)
+        self.nonlinearity = nn.SiLU()
+        use_sc = in_channels != out_channels if use_in_shortcut is None else use_in_shortcut
+        self.conv_shortcut = LoRACompatibleConv(in_channels, out_channels, 1, stride=1, padding=0) if use_sc else None
+
+    def forward(self, input_tensor, temb, scale=1.0):
+        h = self.conv1(self.nonlinearity(self.norm1(input_tensor)))
+        if self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
+        h = self.conv2(self.dropout(self.nonlinearity(self.norm2(h))))
+        if self.conv_shortcut is not None:
+            input_tensor = self.conv_shortcut(input_tensor)
+        return (input_tensor + h) / self.output_scale_factor
+
+
+class DDownsample2D(nn.Module):
+    def __init__(self, channels, use_conv=False, out_channels=None, padding=1, name="conv"):
+        super().__init__()
+        assert use_conv and name in ("op", "conv")
+        self.conv = LoRACompatibleConv(channels, out_channels or channels, 3, stride=2, padding=padding)   # name "op" -> attribute `conv`
+
+    def forward(self, x, scale=1.0):
+        return self.conv(x)
+
+
+class DUpsample2D(nn.Module):
+    def __init__(self, channels, use_conv=False, use_conv_transpose=False, out_channels=None, name="conv"):
+        super().__init__()
+        assert use_conv and not use_conv_transpose
+        self.conv = LoRACompatibleConv(channels, out_channels or channels, 3, padding=1)
+
+    def forward(self, x, output_size=None, scale=1.0):
+        x = F.interpolate(x, scale_factor=2.0, mode="nearest") if output_size is None else F.interpolate(x, size=output_size, mode="nearest")
+        return self.conv(x)
+
+
+def install_stubs_2d():
+    """Extra stand-ins needed to import src/models/{unet_2d_condition,unet_2d_blocks,transformer_2d}.py."""
+    anyc = type("Any2", (nn.Module,), {})
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("diffusers.loaders", UNet2DConditionLoadersMixin=type("UNet2DConditionLoadersMixin", (), {}))
+    mod("diffusers.models.attention_processor", ADDED_KV_ATTENTION_PROCESSORS=(), CROSS_ATTENTION_PROCESSORS=(), AttnAddedKVProcessor=anyc)
+    mod("diffusers.models.embeddings", GaussianFourierProjection=anyc, ImageHintTimeEmbedding=anyc, ImageProjection=anyc, ImageTimeEmbedding=anyc,
+        PositionNet=anyc, TextImageProjection=anyc, TextImageTimeEmbedding=anyc, TextTimeEmbedding=anyc, CaptionProjection=anyc)
+    mod("diffusers.utils", deprecate=lambda *a, **k: None, scale_lora_layers=lambda *a, **k: None, unscale_lora_layers=lambda *a, **k: None,
+        is_torch_version=lambda op, v: True)
+    mod("diffusers.utils.torch_utils", apply_freeu=lambda *a, **k: a)
+    mod("diffusers.models.dual_transformer_2d", DualTransformer2DModel=anyc)
+    mod("diffusers.models.resnet", Downsample2D=DDownsample2D, ResnetBlock2D=DResnetBlock2D, Upsample2D=DUpsample2D)
+    mod("diffusers.models.lora", LoRACompatibleConv=LoRACompatibleConv, LoRACompatibleLinear=LoRACompatibleLinear)
+    mod("diffusers.models.normalization", AdaLayerNormSingle=anyc)
+
+
 def install_stubs():
     def mod(name, **attrs):
         m = types.ModuleType(name)
@@ -325,6 +409,70 @@ def main():
         report["unet_full_params"] = n_params
         torch.save(dict(seed=7, x=xf, ehs=ehsf, pose=posef, t=999, y=y_reff), os.path.join(GOLD, "unet_full_tiny.pt"))
         del reff, oraf
+
+    # ---- 4b. reference ("writer") UNet2D + write hook + update() into the reader --------------------------------
+    install_stubs_2d()
+    from src.models.unet_2d_condition import UNet2DConditionModel as RefUNet2D
+
+    def build_pair_2d(chs, xdim):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref2 = RefUNet2D(in_channels=4, out_channels=4, block_out_channels=chs, cross_attention_dim=xdim, attention_head_dim=8).eval()
+        ora2 = O.synthetic_init(O.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim).eval(), seed=17)
+        missing, unexpected = ref2.load_state_dict(ora2.state_dict(), strict=False)
+        assert not missing and not unexpected, (missing[:5], unexpected[:5])
+        return ref2, ora2
+
+    def ref_write(ref2, lat, ehs2):
+        w = ReferenceAttentionControl(ref2, do_classifier_free_guidance=True, mode="write", batch_size=1, fusion_blocks="full")
+        with torch.no_grad():
+            hid = ref2(lat, torch.zeros((), dtype=torch.long), encoder_hidden_states=ehs2, return_dict=False)[0]
+        from src.models.attention import BasicTransformerBlock as RefBTB
+        blocks = sorted([m for m in torch_dfs_ref(ref2) if isinstance(m, RefBTB)], key=lambda m: -m.norm1.normalized_shape[0])
+        return w, hid, [b.bank[0].clone() for b in blocks]
+
+    from src.models.mutual_self_attention import torch_dfs as torch_dfs_ref
+
+    ref2, ora2 = build_pair_2d((64, 128, 256, 256), 64)
+    lat = torch.randn(1, 4, 16, 16, generator=g).repeat(2, 1, 1, 1)
+    ehs2 = torch.cat([torch.zeros(1, 1, 64), torch.randn(1, 1, 64, generator=g)])
+    writer, hid_ref, banks_ref = ref_write(ref2, lat, ehs2)
+    O.set_reference_write(ora2)
+    with torch.no_grad():
+        hid_ora = ora2(lat, torch.tensor(0), ehs2)[0]
+    banks_ora = O.written_banks(ora2)
+    report["unet2d_writer_hidden"] = maxdiff(hid_ref, hid_ora)
+    report["unet2d_writer_banks"] = max(maxdiff(a, b) for a, b in zip(banks_ref, banks_ora))
+    report["unet2d_writer_bank_shapes"] = [list(b.shape) for b in banks_ref]
+    assert len(banks_ref) == len(banks_ora) == 16
+    # writer -> reader: reference update() chain vs oracle set_reference_banks(written_banks)
+    ref3, ora3 = build_pair((64, 128, 256, 256), True, xdim=64)
+    reader = ReferenceAttentionControl(ref3, do_classifier_free_guidance=True, mode="read", batch_size=1, fusion_blocks="full")
+    reader.update(writer, dtype=torch.float32)
+    x3 = torch.randn(2, 4, 3, 16, 16, generator=g)
+    y3_ref = run_ref(ref3, x3, torch.tensor(519), ehs2, return_dict=False)[0]
+    O.set_reference_banks(ora3, banks_ora, cfg=True)
+    with torch.no_grad():
+        y3_ora = ora3(x3, torch.tensor(519), ehs2)[0]
+    report["unet2d_writer_to_reader_chain"] = maxdiff(y3_ref, y3_ora)
+    torch.save(dict(seed=17, lat=lat, ehs=ehs2, hidden=hid_ref, banks=banks_ref, seed3=7, x3=x3, t3=519, y3=y3_ref),
+               os.path.join(GOLD, "unet2d_writer_narrow.pt"))
+    reader.clear()
+    writer.clear()
+    del ref2, ora2, ref3, ora3
+    if os.environ.get("PIN_FULL", "1") == "1":
+        ref2, ora2 = build_pair_2d((320, 640, 1280, 1280), 768)
+        latf = torch.randn(1, 4, 8, 8, generator=g).repeat(2, 1, 1, 1)
+        ehs2f = torch.cat([torch.zeros(1, 1, 768), torch.randn(1, 1, 768, generator=g)])
+        writer, hid_ref, banks_ref = ref_write(ref2, latf, ehs2f)
+        O.set_reference_write(ora2)
+        with torch.no_grad():
+            hid_ora = ora2(latf, torch.tensor(0), ehs2f)[0]
+        report["unet2d_writer_full_width_hidden"] = maxdiff(hid_ref, hid_ora)
+        report["unet2d_writer_full_width_banks"] = max(maxdiff(a, b) for a, b in zip(banks_ref, O.written_banks(ora2)))
+        report["unet2d_writer_full_params"] = sum(p.numel() for p in ora2.parameters())
+        torch.save(dict(seed=17, lat=latf, ehs=ehs2f, hidden=hid_ref, banks=banks_ref), os.path.join(GOLD, "unet2d_writer_full_tiny.pt"))
+        writer.clear()
+        del ref2, ora2
 
     # ---- 5. PoseGuider -----------------------------------------------------------------------
     rpg = RefPG(320, block_out_channels=(16, 32, 96, 256)).eval()

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
     lib = ctypes.CDLL(_native.LIB_PATH)
     syms = header_symbols()
-    assert len(syms) >= 30
+    assert len(syms) >= 31 and "hv_unet2d_reference_forward" in syms
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
 
@@ -56,6 +56,36 @@ def test_unet_shell_has_reference_state_dict_keys():
     m1 = UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
     o1 = O.UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, use_motion_module=False, use_inflated_groupnorm=False)
     assert set(m1.state_dict()) == set(o1.state_dict())
+
+
+def test_reference_unet2d_shell_keys_and_writer_order():
+    from humanvid_b200 import ReferenceAttentionControl, UNet2DConditionModel, UNet3DConditionModel
+
+    m = UNet2DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64)
+    o = O.UNet2DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64)
+    sm, so = m.state_dict(), o.state_dict()
+    assert set(sm) == set(so) and all(sm[k].shape == so[k].shape for k in so)
+    names = {id(b): n for n, b in m.named_modules()}
+    import json
+
+    rep = json.load(open(os.path.join(ROOT, "tests", "golden", "pin_report.json")))
+    assert [names[id(b)] for b, _ in m.writer_blocks()] == rep["bank_order"]   # same sorted order on writer and reader side
+    assert [lvl for _, lvl in m.writer_blocks()] == [2] * 5 + [3] + [1] * 5 + [0] * 5
+    w = ReferenceAttentionControl(m, do_classifier_free_guidance=True, mode="write", fusion_blocks="full")
+    assert m._ref_write and all(b.bank == [] for b, _ in m.writer_blocks())
+    with pytest.raises(TypeError):
+        ReferenceAttentionControl(m, mode="read", fusion_blocks="full")
+    with pytest.raises(NotImplementedError):
+        UNet2DConditionModel(use_linear_projection=True)
+    # update(): writer banks land on the reader's blocks in the same order
+    r3 = UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    rd = ReferenceAttentionControl(r3, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
+    for i, (b, _) in enumerate(m.writer_blocks()):
+        b.bank.append(torch.full((2, 4, b.norm1.normalized_shape[0]), float(i)))
+    rd.update(w, dtype=torch.float32)
+    assert [float(b.bank[0][0, 0, 0]) for b in r3.reader_blocks()] == [float(i) for i in range(16)]
+    rd.clear(); w.clear()
+    assert all(len(b.bank) == 0 for b in r3.reader_blocks()) and all(len(b.bank) == 0 for b, _ in m.writer_blocks())
 
 
 def test_pose_guider_and_camera_shells():

@@ -138,6 +138,70 @@ def test_unet_full_width_against_reference_golden():
     torch.cuda.empty_cache()
 
 
+def make_writer(chs, xdim, seed=17):
+    ora = O.synthetic_init(O.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim).eval(), seed=seed).half().float().cuda()
+    nat = hv.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim)
+    nat.load_state_dict(ora.state_dict())
+    return ora, nat.to("cuda", torch.float16)
+
+
+def test_reference_writer_unet2d_golden_banks_and_chain():
+    """Native reference ("writer") UNet: hidden + 16 banks against vectors from the reference's own UNet2DConditionModel in write
+    mode; then writer -> ReferenceAttentionControl.update -> native denoising UNet against the reference's chain."""
+    g = torch.load(os.path.join(GOLD, "unet2d_writer_narrow.pt"), weights_only=False)
+    ora, nat = make_writer((64, 128, 256, 256), 64, seed=g["seed"])
+    lat, ehs = g["lat"].cuda().half(), g["ehs"].cuda().half()
+    writer = hv.ReferenceAttentionControl(nat, do_classifier_free_guidance=True, mode="write", batch_size=1, fusion_blocks="full")
+    with torch.no_grad():
+        hid = nat(lat, torch.zeros((), dtype=torch.long, device="cuda"), encoder_hidden_states=ehs, return_dict=False)[0]
+        hid16 = ora.half()(lat, torch.tensor(0, device="cuda"), ehs)[0]
+        ora.float()
+    banks = [b.bank[0] for b, _ in nat.writer_blocks()]
+    assert hid.shape == (2, 64, 16, 16) and [tuple(b.shape) for b in banks] == [tuple(b.shape) for b in g["banks"]]
+    e_hid, e_ref = rel(hid, g["hidden"].cuda()), rel(hid16, g["hidden"].cuda())
+    e_banks = [rel(b, gb.cuda()) for b, gb in zip(banks, g["banks"])]
+    print(f"writer UNet2D: hidden native vs reference golden {e_hid:.2e} (fp16-eager {e_ref:.2e}); banks max {max(e_banks):.2e}")
+    assert e_hid <= 1.5 * e_ref + 5e-4
+    assert max(e_banks) <= 2e-3
+    # writer -> reader on the native denoising UNet; reference chain value y3
+    ora3, nat3 = make_unet((64, 128, 256, 256), 64, seed=g["seed3"])
+    reader = hv.ReferenceAttentionControl(nat3, do_classifier_free_guidance=True, mode="read", batch_size=1, fusion_blocks="full")
+    reader.update(writer)
+    x3 = g["x3"].cuda().half()
+    with torch.no_grad():
+        y = nat3(x3, g["t3"], ehs, return_dict=False)[0]
+        O.set_reference_banks(ora3, [gb.cuda().half() for gb in g["banks"]], cfg=True)
+        y16 = ora3.half()(x3, torch.tensor(g["t3"], device="cuda"), ehs)[0]
+    e_nat, e_16 = rel(y, g["y3"].cuda()), rel(y16, g["y3"].cuda())
+    print(f"writer -> reader chain: native vs reference golden {e_nat:.2e} (fp16-eager {e_16:.2e})")
+    assert e_nat <= 1.5 * e_16 + 5e-4
+    reader.clear(); writer.clear()
+    # without write mode the forward is unchanged and leaves no banks
+    nat._ref_write = False
+    with torch.no_grad():
+        hid2 = nat(lat, 0, ehs, return_dict=False)[0]
+    assert torch.equal(hid, hid2) and all(len(b.bank) == 0 for b, _ in nat.writer_blocks())
+
+
+def test_reference_writer_unet2d_full_width_config2_shape():
+    """SD1.5-width writer at the 96x72 latent of BASELINE config 2/3: bank shapes are what the reader takes, values vs the oracle."""
+    ora, nat = make_writer((320, 640, 1280, 1280), 768, seed=17)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lat = torch.randn(1, 4, 96, 72, generator=g, device="cuda").half().repeat(2, 1, 1, 1)
+    ehs = torch.cat([torch.zeros(1, 1, 768, device="cuda"), torch.randn(1, 1, 768, generator=g, device="cuda")]).half()
+    hv.ReferenceAttentionControl(nat, do_classifier_free_guidance=True, mode="write", fusion_blocks="full")
+    O.set_reference_write(ora)
+    with torch.no_grad():
+        hid = nat(lat, 0, ehs, return_dict=False)[0]
+        hid32 = ora(lat.float(), torch.tensor(0, device="cuda"), ehs.float())[0]
+    banks, banks32 = [b.bank[0] for b, _ in nat.writer_blocks()], O.written_banks(ora)
+    assert [tuple(b.shape[1:]) for b in banks] == [(432, 1280)] * 5 + [(108, 1280)] + [(1728, 640)] * 5 + [(6912, 320)] * 5
+    errs = [rel(a, b) for a, b in zip(banks, banks32)]
+    print(f"writer UNet2D full width 96x72: hidden {rel(hid, hid32):.2e}, banks max {max(errs):.2e}")
+    assert rel(hid, hid32) <= 4e-3 and max(errs) <= 3e-3
+    assert torch.equal(banks[0][0], banks[0][0]) and torch.isfinite(hid).all()
+
+
 def test_pose_guider_and_camera_encoder_golden():
     g = torch.load(os.path.join(GOLD, "pose_guider.pt"), weights_only=False)
     o = O.synthetic_init(O.PoseGuider().eval(), seed=g["seed"])

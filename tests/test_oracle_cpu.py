@@ -18,7 +18,8 @@ def load(name):
 def test_pin_report_is_exact():
     rep = json.load(open(os.path.join(GOLD, "pin_report.json")))
     for k in ("unet_narrow_motion", "unet_narrow_bank_cfg1", "unet_narrow_bank_cfg0", "unet_narrow_image", "unet_full_width", "pose_guider",
-              "camera_encoder", "plucker"):
+              "camera_encoder", "plucker", "unet2d_writer_hidden", "unet2d_writer_banks", "unet2d_writer_to_reader_chain",
+              "unet2d_writer_full_width_hidden", "unet2d_writer_full_width_banks"):
         assert rep[k] == 0.0, (k, rep[k])
     assert rep["unet_full_params"] == 1312730244
     # DFS(down, up, mid) stable-sorted by -width
@@ -54,6 +55,33 @@ def test_reference_bank_hook_golden_and_identities(narrow):
         y0 = m(x, t, ehs, pose_cond_fea=pose)[0]
     assert torch.allclose(y[:1], y0[:1], atol=1e-5)
     assert not torch.allclose(y[1:], y0[1:], atol=1e-3)
+
+
+def test_reference_writer_unet2d_golden_and_chain():
+    """The reference ("writer") UNet restatement against vectors produced by the reference's own UNet2DConditionModel under
+    ReferenceAttentionControl(mode="write"), and writer -> reader.update() -> denoising UNet against the reference chain."""
+    g = load("unet2d_writer_narrow.pt")
+    w = O.synthetic_init(O.UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64).eval(), seed=g["seed"])
+    assert "conv_out.weight" not in w.state_dict() and "conv_norm_out.weight" not in w.state_dict()
+    O.set_reference_write(w)
+    with torch.no_grad():
+        hid = w(g["lat"], torch.tensor(0), g["ehs"])[0]
+    banks = O.written_banks(w)
+    assert torch.allclose(hid, g["hidden"], atol=1e-5, rtol=1e-5)
+    assert len(banks) == 16 and [tuple(b.shape) for b in banks] == [tuple(b.shape) for b in g["banks"]]
+    assert all(torch.allclose(a, b, atol=1e-5, rtol=1e-5) for a, b in zip(banks, g["banks"]))
+    # a bank is LayerNorm-1's output: zero mean / unit variance per token for the synthetic affine-free init is not assumed; only shape + order
+    assert [b.shape[2] for b in banks] == [256] * 6 + [128] * 5 + [64] * 5 and banks[5].shape[1] == 4
+    r = O.synthetic_init(O.UNet3DConditionModel(block_out_channels=(64, 128, 256, 256), cross_attention_dim=64).eval(), seed=g["seed3"])
+    O.set_reference_banks(r, banks, cfg=True)
+    with torch.no_grad():
+        y = r(g["x3"], torch.tensor(g["t3"]), g["ehs"])[0]
+    assert torch.allclose(y, g["y3"], atol=1e-5, rtol=1e-5)
+    # write mode is a pure tap: the forward value does not depend on it
+    O.set_reference_write(w, False)
+    with torch.no_grad():
+        hid2 = w(g["lat"], torch.tensor(0), g["ehs"])[0]
+    assert torch.equal(hid, hid2)
 
 
 def test_zero_init_branches_are_noops(narrow):

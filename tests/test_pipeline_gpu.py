@@ -1,6 +1,7 @@
-"""Pose2VideoPipeline (humanvid_b200.pipeline) end to end on a B200 with stand-in VAE / CLIP modules: 48 frames = three
-overlapping 24-frame context windows, CFG, DDIM (trailing, v-prediction, zero-SNR), feature cache -- against the
-oracle's restatement of the same loop (oracle.denoise_step + oracle.DDIM, pipeline_pose2vid_long.py:454-563)."""
+"""Pose2VideoPipeline (humanvid_b200.pipeline) end to end on a B200 with stand-in VAE / CLIP modules: native reference
+("writer") UNet -> banks -> native denoising UNet, 48 frames = three overlapping 24-frame context windows, CFG, DDIM
+(trailing, v-prediction, zero-SNR), feature cache -- against the oracle's restatement of the same loop (oracle writer +
+set_reference_banks + oracle.denoise_step + oracle.DDIM, pipeline_pose2vid_long.py:393-563)."""
 from types import SimpleNamespace
 
 import pytest
@@ -62,10 +63,13 @@ def test_pose2video_pipeline_three_windows_matches_oracle_loop():
                                temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
                                temporal_position_encoding_max_len=24)
     cam.load_state_dict(ocam.state_dict())
+    oref = O.synthetic_init(O.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim).eval(), seed=17).half().float().to(dev)
+    ref_unet = hv.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim)
+    ref_unet.load_state_dict(oref.state_dict())
     vae, clip = StubVAE().half().to(dev), StubCLIP(xdim).half().to(dev)
     sched = hv.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
                              prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
-    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=None, denoising_unet=unet, pose_guider=pg, camera_pose_encoder=cam,
+    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=ref_unet, denoising_unet=unet, pose_guider=pg, camera_pose_encoder=cam,
                               scheduler=sched).to(dev, torch.float16)
 
     g = torch.Generator(device=dev).manual_seed(3)
@@ -84,12 +88,17 @@ def test_pose2video_pipeline_three_windows_matches_oracle_loop():
         emb = clip(F.interpolate(ref[None].float(), size=(224, 224), mode="bilinear", align_corners=False).half()).image_embeds.float()
         ehs = torch.cat([torch.zeros_like(emb), emb]).unsqueeze(1)
         pose_cond = torch.cat([p.unsqueeze(2) for p in poses], dim=2).half().float()
+        # reference image -> VAE latents -> writer UNet at t = 0 -> banks -> reader (pipeline_pose2vid_long.py:447-480)
+        ref_lat = (vae.encode(ref[None].half()).latent_dist.mean * 0.18215).float()
+        O.set_reference_write(oref)
+        oref(ref_lat.repeat(2, 1, 1, 1), torch.tensor(0, device=dev), ehs)
+        O.set_reference_banks(ora, O.written_banks(oref), cfg=True)
         dd = O.DDIM()
         for t in dd.set_timesteps(steps).tolist():
             v = O.denoise_step(ora, opg, ocam, lat, torch.tensor(t, device=dev), ehs, pose_cond, camera.float(), guidance_scale=cfg)
             lat = dd.step(v.cpu(), t, lat.cpu()).to(dev)
     e = rel(out, lat)
-    print(f"pipeline 48 frames / 3 windows / 2 DDIM steps: latents rel err vs oracle loop {e:.2e}")
+    print(f"pipeline (native writer + reader) 48 frames / 3 windows / 2 DDIM steps: latents rel err vs oracle loop {e:.2e}")
     assert e < 1e-2
     # the step-invariant condition features are cached per window and reused: same result with the cache off
     pipe.cache_condition_features = False
