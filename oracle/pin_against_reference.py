@@ -5,7 +5,8 @@ Run in the build container only (needs /root/reference):
     python oracle/pin_against_reference.py            # check + (re)write tests/golden/*.pt
 
 What is the real reference here: src/models/{unet_3d,unet_3d_blocks,resnet,transformer_3d,
-attention,motion_module,mutual_self_attention,pose_guider}.py, src/cameractrl/{pose_adaptor,
+attention,motion_module,mutual_self_attention,pose_guider}.py, the 2-D reference ("writer") UNet
+src/models/{unet_2d_condition,unet_2d_blocks,transformer_2d}.py with the write hook and reader.update(writer), src/cameractrl/{pose_adaptor,
 motion_module}.py, src/pipelines/context.py, src/dataset/dance_image_h_v_camera.py
 (Camera, ray_condition) and scripts/pose2vid.py's get_relative_pose logic -- imported
 unmodified from /root/reference.
