@@ -119,7 +119,9 @@ def pick_cpu_threads():
         ncpu = min(ncpu, len(os.sched_getaffinity(0)))
     except AttributeError:
         pass
-    cands = sorted({c for c in (ncpu, 96, 64, 48, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    # never all logical CPUs: one box ran the full model 20x slower on 128 threads than on 64 although the probe liked 128
+    top = max(1, ncpu // 2)
+    cands = sorted({c for c in (top, 64, 48, 32, 16, 8) if 1 <= c <= top}, reverse=True)
     x = torch.randn(1, 320, H // 2, W // 2)
     w = torch.randn(320, 320, 3, 3) * 0.02
     a = torch.randn(H * W // 4, 1280)

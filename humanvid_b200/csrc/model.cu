@@ -108,7 +108,10 @@ struct SpatialW {
   Lin ff1, ff2;  // ff1 geglu-packed
   int C = 0, heads = 0, d = 0, dpad = 0;
   int reader_idx = -1;
-  // reference bank (B_ref, L, C)
+  // reference bank (B_ref, L, C): `bank` is non-null while a bank is set; its storage (bank_store, bank_cap elements) is kept
+  // across hv_clear_ref_banks so that the per-forward clear / set of the Python reader costs no allocation
+  __half* bank_store = nullptr;
+  int64_t bank_cap = 0;
   __half* bank = nullptr;
   int64_t bank_B = 0, bank_L = 0;
   std::string name;
@@ -993,7 +996,11 @@ int hv_set_ref_bank(hv_handle h, int32_t idx, const void* dev_ptr, int64_t B_ref
     SpatialW* w = h->readers[idx];
     if (C != w->C) fail(HV_ERR_INVALID, "bank %d has width %lld, block '%s' has %d", idx, (long long)C, w->name.c_str(), w->C);
     const int64_t n = B_ref * L * C;
-    if (w->bank == nullptr || w->bank_B * w->bank_L != B_ref * L) w->bank = h->dmalloc(n);
+    if (w->bank_cap < n) {
+      w->bank_store = h->dmalloc(n);
+      w->bank_cap = n;
+    }
+    w->bank = w->bank_store;
     w->bank_B = B_ref;
     w->bank_L = L;
     ck(cudaMemcpyAsync(w->bank, dev_ptr, static_cast<size_t>(n) * 2, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "bank copy");
@@ -1003,7 +1010,7 @@ int hv_set_ref_bank(hv_handle h, int32_t idx, const void* dev_ptr, int64_t B_ref
 int hv_clear_ref_banks(hv_handle h) {
   if (!h) return HV_ERR_INVALID;
   for (SpatialW* w : h->readers) {
-    w->bank = nullptr;  // storage stays in `owned` and is released with the handle
+    w->bank = nullptr;  // bank_store is kept for the next hv_set_ref_bank
     w->bank_B = w->bank_L = 0;
   }
   return HV_OK;

@@ -412,6 +412,13 @@ class UNet3DConditionModel(_NativeNet):
         lib = N.lib()
         blocks = self.reader_blocks()
         any_bank = any(len(b.bank) > 0 for b in blocks)
+        # the banks are step-invariant (written once per clip): skip the 16 device copies when nothing changed since the last push
+        # (the pushed tensors are kept referenced so that their addresses cannot be recycled under the fingerprint)
+        tensors = [t for b in blocks for t in b.bank]
+        fp = (h.value if hasattr(h, "value") else h, self._epoch) + tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in tensors)
+        if getattr(self, "_bank_fp", None) == fp:
+            return
+        self._bank_fp, self._bank_refs = fp, tensors
         N.check(lib.hv_clear_ref_banks(h), h)
         if not any_bank:
             return
