@@ -151,10 +151,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int num_tiles = m_tiles * n_tiles;
   const int nkb = p.num_k_blocks;
 
+  // 2-CTA cluster along N (p.cluster): the partner CTAs work on tiles t, t+1 of the same m-block (n_tiles and gridDim.x are
+  // even), each loads 64 of the A tile's 128 rows and multicasts them into both CTAs' rings -> half the TMA requests per CTA
+  // for A.  A ring slot may be refilled only when BOTH CTAs have consumed it: the MMA warps commit to both empty barriers.
+  const uint32_t crank = p.cluster ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_empty[s], p.cluster ? 2 : 1);
     }
     mbar_init(bar_bpanel, 1);
     for (int s = 0; s < 16; ++s) mbar_init(&bar_res[s], 1);
@@ -174,6 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync();   // the partner's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -216,7 +221,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           uint8_t* sa = ring + stage * kRingStageBytes;
           uint8_t* sb = sa + C::kATileBytes;
           mbar_arrive_expect_tx(&bar_full[stage], kRingStageBytes);
-          if (p.a_mode == A_LINEAR) {
+          if (p.a_mode == A_LINEAR && p.cluster) {
+            uint8_t* half = sa + crank * (A_TILE_BYTES / 2);   // rows 64*crank .. +63 of the tile (SW128 pattern repeats every 8 rows)
+            if (p.k_split == 0 || kb < p.k_split)
+              tma_load_2d_mc(half, &map_a0, &bar_full[stage], kb * BLOCK_K, tc.m0 + crank * (BLOCK_M / 2), 0x3);
+            else
+              tma_load_2d_mc(half, &map_a1, &bar_full[stage], (kb - p.k_split) * BLOCK_K, tc.m0 + crank * (BLOCK_M / 2), 0x3);
+          } else if (p.a_mode == A_LINEAR) {
             if (p.k_split == 0 || kb < p.k_split)
               tma_load_2d(sa, &map_a0, &bar_full[stage], kb * BLOCK_K, tc.m0);
             else
@@ -268,7 +279,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             for (int k = 0; k < BLOCK_K / 16; ++k)
               umma_f16_ss_w(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_w(&bar_empty[stage]);
+          if (p.cluster) umma_commit_mc_w(&bar_empty[stage], 0x3);
+          else umma_commit_w(&bar_empty[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit_w(&bar_tfull[acc]);
@@ -619,6 +631,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync();   // no CTA leaves while its partner may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -657,6 +670,21 @@ static cudaError_t launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const 
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
+  if (p.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid & ~1, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<BN, MT>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, MT, false>, a0, a1, b, mo, mr, p, e);
+  }
   gemm_kernel<BN, MT, false><<<grid, GEMM_THREADS, Cfg<BN, MT>::kSmemBytes, stream>>>(a0, a1, b, mo, mr, p, e);
   return cudaGetLastError();
 }
@@ -679,8 +707,30 @@ static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, cons
   }
   p.bst_stages = stages;
   const int smem = panel + stages * C::kATileBytes + C::kBstFixed;
+  if (p.cluster) {   // n_tiles is even, so the grid (a multiple of n_tiles) is too
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(per_col * n_tiles, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_kernel<BN, 1, true>, a0, a1, b, mo, mr, p, e);
+  }
   gemm_kernel<BN, 1, true><<<per_col * n_tiles, GEMM_THREADS, smem, stream>>>(a0, a1, b, mo, mr, p, e);
   return cudaGetLastError();
+}
+
+bool gemm_wants_cluster(int64_t M, int64_t N, int block_n, int m_sub, bool batched_b) {
+  static const int env = [] { const char* v = getenv("HV_GEMM_CLUSTER"); return v ? atoi(v) : 0; }();
+  if (!env || m_sub != 1 || batched_b) return false;
+  const int64_t n_tiles = (N + block_n - 1) / block_n, m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  return (n_tiles % 2) == 0 && m_tiles * n_tiles >= 2 * 148;   // pairs exist and the persistent grid is full
 }
 
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p_in,
@@ -689,6 +739,8 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   static const int pf_env = [] { const char* v = getenv("HV_GEMM_PF"); return v ? atoi(v) : 0; }();  // experiment, off: the extra TMA requests cost more than the latency they hide
   GemmProblem p = p_in;
   p.pf_dist = pf_env;
+  if (p.cluster && !(m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && gemm_wants_cluster(p.M, p.N, block_n, m_sub, false)))
+    return cudaErrorInvalidValue;   // the caller built 64-row A boxes for a launch that cannot use them
   GemmEpilogue e = e_in;
   e.tma_io = (io_out != nullptr && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && (e.residual == nullptr || e.geglu || io_res != nullptr)) ? 1 : 0;
   const CUtensorMap& mo = e.tma_io ? *io_out : a0;
@@ -700,7 +752,8 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   if (tiles <= 0 || p.num_k_blocks <= 0) return cudaErrorInvalidValue;
   if (p.b_batch && (e.bias || e.rowvec || e.residual || e.geglu || (p.b_out_stride % 8))) return cudaErrorInvalidValue;
   if (e.geglu && block_n != 256) return cudaErrorInvalidValue;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (p.cluster) grid &= ~1;
   static const int bst_env = [] { const char* v = getenv("HV_GEMM_BST"); return v ? atoi(v) : 1; }();
   if (bst_env && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && n_tiles <= num_sms) {
     cudaError_t r = cudaErrorNotSupported;

@@ -32,6 +32,7 @@ struct GemmProblem {
   int num_k_blocks = 0;            // ceil(K / 64)
   int bst_stages = 0;              // set by launch_gemm: A-ring depth of the B-stationary variant
   int pf_dist = 0;                 // set by launch_gemm: the producer prefetches A boxes this many k-blocks ahead into L2
+  int cluster = 0;                 // 2-CTA clusters along N: each CTA loads half of the shared A tile (64-row box) and multicasts it
   int a_mode = A_LINEAR;
   int k_split = 0;                 // A_LINEAR: k-blocks taken from tensor map a0 (rest from a1); 0 = all from a0
   int cin_blocks = 0;              // conv: 64-channel blocks per tap
@@ -54,6 +55,9 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
                         const GemmEpilogue& e, int block_n, int num_sms, cudaStream_t stream, int m_sub = 1,
                         const CUtensorMap* io_out = nullptr, const CUtensorMap* io_res = nullptr);
 inline int gemm_io_box_cols(int block_n, bool geglu) { return geglu ? block_n / 8 : block_n / 4; }
+// Experimental (HV_GEMM_CLUSTER=1, default off, not yet validated on hardware): pairs of CTAs with the same m-block share the A
+// tile through TMA multicast; the caller must then build the A map(s) with 64-row boxes.  True when this launch would use it.
+bool gemm_wants_cluster(int64_t M, int64_t N, int block_n, int m_sub, bool batched_b);
 
 // Picks the (bn, bh, bw) output-tile box with the least padding for an NF x H x W output.
 // (rows = 128 or 256 output pixels per CTA tile; every box dimension is a power of two <= 256)

@@ -111,9 +111,11 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   const int64_t m_tiles = (M + 127) / 128;
   const int bn = pick_block_n(N, m_tiles, geglu, sms);
   const int m_sub = pick_m_sub(M, N, bn, K, sms);
-  if (!make_map_2d(&ma0, A, M, Ka, lda, 128 * m_sub)) { set_error("hv_op_gemm A map: %s", tma_last_error()); return HV_ERR_TMA; }
+  const bool cluster = gemm_wants_cluster(M, N, bn, m_sub, false);
+  const int a_box_rows = cluster ? 64 : 128 * m_sub;   // clustered launch: each CTA fetches (and multicasts) half of the A tile
+  if (!make_map_2d(&ma0, A, M, Ka, lda, a_box_rows)) { set_error("hv_op_gemm A map: %s", tma_last_error()); return HV_ERR_TMA; }
   ma1 = ma0;
-  if (split && !make_map_2d(&ma1, A2, M, K - K1, lda2, 128 * m_sub)) { set_error("hv_op_gemm A2 map: %s", tma_last_error()); return HV_ERR_TMA; }
+  if (split && !make_map_2d(&ma1, A2, M, K - K1, lda2, a_box_rows)) { set_error("hv_op_gemm A2 map: %s", tma_last_error()); return HV_ERR_TMA; }
   if (!make_map_2d(&mb, W, N, K, K, bn)) { set_error("hv_op_gemm W map: %s", tma_last_error()); return HV_ERR_TMA; }
   GemmProblem p;
   p.M = static_cast<int>(M);
@@ -121,6 +123,7 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   p.num_k_blocks = static_cast<int>((K + 63) / 64);
   p.a_mode = A_LINEAR;
   p.k_split = split ? static_cast<int>(K1 / 64) : 0;
+  p.cluster = cluster ? 1 : 0;
   GemmEpilogue e;
   fill_epilogue(e, ep, out, ldc, N);
   // 128-row tiles: the output (and residual) slices move by TMA through per-warp shared-memory boxes
