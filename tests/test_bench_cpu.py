@@ -1,0 +1,24 @@
+"""bench.py's reference arm (the oracle timed on the host cores) runs without a GPU: check the JSON contract of its line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_contract_line():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] > 0 and abs(line["value"] - line["cpu_baseline"]["value"]) < 1e-12 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and 1 <= cb["cores"] <= max(1, (os.cpu_count() or 2) // 2) and "frame-pass" in cb["sample"]
+    assert "workload" in line["config"] and "model" not in line["config"]
