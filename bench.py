@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- denoising-UNet frames/sec at BASELINE config 2 (one clip: 24 frames of 768x576, CFG batch 2, fp16).
+"""bench.py -- denoising-UNet frames/sec of the CamAnimate denoising path on B200 (BASELINE.json configs 2-5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--banks 0|1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one per-timestep pass of the hot path for one clip: UNet3DConditionModel.forward on (2,4,24,96,72) latents
-(CFG-doubled), encoder_hidden_states (2,1,768) and pose_cond_fea (2,320,24,96,72).  value = clips * 24 frames / t_step.
+Workloads; default: config 2 on one GPU, config 4 under N > 1:
+  config 2   1 clip, 24 frames of 768x576 (latent 96x72), CFG batch 2, no reference bank          96.30 TFLOP / step
+  config 3   the same clip with the 16 ReferenceAttentionControl K/V banks                         105.71 TFLOP / step
+  config 4   N independent config-3 clips, one per GPU, one final all-gather (weak scaling)        N x 105.71
+  config 5   1 clip, 48 frames of 576x1024 (latent 72x128) = three 24-frame context windows per    3 x 152.11
+             timestep, banks on; N > 1 splits the 6 (window x CFG-half) units over ranks (strong scaling)
+A "step" is one per-timestep pass of the hot path for the clip(s): configs 2-4 one UNet3DConditionModel.forward on the
+CFG-doubled batch; config 5 the three window forwards plus the on-device accumulate / CFG / DDIM glue.
+value = frames of all clips / t_step.
 
-  native arm     humanvid_b200 (hand-written sm_100a CUDA through the C ABI).  `value`: inputs resident in HBM, device
-                 time (CUDA events) of K back-to-back forwards.  `e2e`: the public Python call with the step's latents
-                 copied from pinned host memory and the prediction read back to the host every step.
-  reference arm  (--impl reference) the reference-equivalent PyTorch path (the oracle; the reference itself cannot be
-                 imported: diffusers is not installed) in fp32 on the host CPU cores, on a bounded sample of the same
-                 workload: 1 of the step's 48 frame-passes at full 96x72 latent resolution (all spatial work is per
-                 frame; the temporal attention, degenerate on one frame, is 0.2 % of the FLOPs), scaled linearly in
-                 frame-passes (~30 s per sample on 128 cores; the whole step would take ~25 min).
+  native arm     humanvid_b200 (hand-written sm_100a CUDA through the C ABI).  `value`: inputs resident in HBM, device time (CUDA
+                 events) of K back-to-back steps, max over ranks.  `e2e`: the public Python call with the step's latents copied from
+                 pinned host memory and the result read back to the host every step.  `oracle_gpu_eager`: the library bar -- the
+                 reference-equivalent PyTorch path (the oracle) in fp16 eager on the same GPU and inputs.
+  reference arm  (--impl reference) the oracle in fp32 on the host CPU cores, on a bounded sample of the same workload: 4 of the
+                 step's frame-passes (2 frames x 2 CFG halves) at the full latent resolution, scaled linearly in frame-passes.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -29,13 +35,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-F, H, W = 24, 96, 72
 CH = (320, 640, 1280, 1280)
 XDIM = 768
-FLOPS_CFG2 = 96.30e12   # algorithmic 2*MAC per UNet forward, no bank
-FLOPS_CFG3 = 105.71e12  # with the 16 reference banks
 MM_KW = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
              temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+# frames of the clip, frames per window, latent h x w, banks, algorithmic TFLOP per UNet forward, windows per step
+CONFIGS = {
+    2: dict(frames=24, fw=24, h=96, w=72, banks=False, tflop_fwd=96.30, windows=1, name="config2"),
+    3: dict(frames=24, fw=24, h=96, w=72, banks=True, tflop_fwd=105.71, windows=1, name="config3"),
+    4: dict(frames=24, fw=24, h=96, w=72, banks=True, tflop_fwd=105.71, windows=1, name="config4"),
+    5: dict(frames=48, fw=24, h=72, w=128, banks=True, tflop_fwd=152.11, windows=3, name="config5"),
+}
 
 
 def peaks():
@@ -44,6 +54,17 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", 1421.9), d.get("bf16_tflops", 1668.4), d.get("hbm_gbs", 6586.4), "measured"
     return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu pass of this command (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 def synthetic_init_(module, seed, device):
@@ -107,102 +128,95 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
-def pick_cpu_threads():
-    """Thread count for the CPU arm: the fastest of a few candidates on a probe of the path's two dominant CPU ops (3x3 conv
-    and token GEMM at level-0 shape).  "All logical CPUs" is not it on the GPU boxes: 128 threads ran the oracle 10x slower
-    than 16 threads do on an 8-core container (OpenMP oversubscription under a CPU quota)."""
-    import torch
-    import torch.nn.functional as Fn
-
-    ncpu = os.cpu_count() or 1
+def cpu_threads():
+    """Pinned (not probed) thread count for the CPU arm, so that repeated runs time the same thing: the CPUs this process may use
+    (affinity mask, cgroup quota), halved on large SMT boxes, capped at 64 -- more threads have run the oracle up to 20x SLOWER on
+    the GPU boxes (OpenMP oversubscription), and a per-run probe made the round-1 baseline wander 3.3x."""
+    n = os.cpu_count() or 1
     try:
-        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+        n = min(n, len(os.sched_getaffinity(0)))
     except AttributeError:
         pass
-    # never all logical CPUs: one box ran the full model 20x slower on 128 threads than on 64 although the probe liked 128
-    top = max(1, ncpu // 2)
-    cands = sorted({c for c in (top, 64, 48, 32, 16, 8) if 1 <= c <= top}, reverse=True)
-    x = torch.randn(1, 320, H // 2, W // 2)
-    w = torch.randn(320, 320, 3, 3) * 0.02
-    a = torch.randn(H * W // 4, 1280)
-    b = torch.randn(1280, 1280) * 0.02
-    best, best_t = cands[-1], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        with torch.no_grad():
-            Fn.conv2d(x, w, padding=1); a @ b   # warm
-            t0 = time.perf_counter()
-            for _ in range(2):
-                Fn.conv2d(x, w, padding=1)
-                a @ b
-            t = time.perf_counter() - t0
-        if t < best_t * 0.95:   # prefer more threads only when clearly faster
-            best, best_t = c, t
-    return best
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, min(64, n // 2 if n > 16 else n))
 
 
-def cpu_reference_sample(steps, warmup, frames=1, cfg_batch=1):
-    """Oracle (reference-equivalent PyTorch, fp32) on the host cores.  One sample = UNet forward over `frames` frames of
-    `cfg_batch` CFG halves at the full 96x72 latent: frames * cfg_batch of the step's 48 frame-passes (~30 s on 128 cores, the
-    whole 48 would take ~25 min).  frames/s counts a frame as the CFG pair of passes, like the native arm."""
+def cpu_reference_sample(cfg, samples=3, warmup=1, frames=2, cfg_batch=2):
+    """Oracle (reference-equivalent PyTorch, fp32) on the host cores.  One sample = a UNet forward over `frames` frames of
+    `cfg_batch` CFG halves at the config's full latent (and with its reference banks): frames * cfg_batch of the step's
+    2 * fw * windows frame-passes.  frames/s counts a video frame as its CFG pair of passes, like the native arm."""
     import torch
 
     from oracle import hv_oracle as O
 
-    nthreads = pick_cpu_threads()
+    nthreads = cpu_threads()
     torch.set_num_threads(nthreads)
     torch.set_flush_denormal(True)   # random-init activations reach denormals in places; the x86 slow path would understate the CPU
+    H, W = cfg["h"], cfg["w"]
     m = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval()
     synthetic_init_(m, 7, "cpu")
     g = torch.Generator().manual_seed(1)
     x = torch.randn(cfg_batch, 4, frames, H, W, generator=g)
     ehs = torch.randn(cfg_batch, 1, XDIM, generator=g)
+    ehs[: cfg_batch // 2] = 0
     pose = torch.randn(cfg_batch, CH[0], frames, H, W, generator=g) * 0.5
+    if cfg["banks"]:
+        O.set_reference_banks(m, [torch.randn(cfg_batch, l, c, generator=g) for (l, c) in O.bank_shapes(m, H, W)], cfg=cfg_batch > 1)
     times = []
     with torch.no_grad():
-        for i in range(warmup + steps):
+        for i in range(warmup + samples):
             t0 = time.perf_counter()
             m(x, torch.tensor(500), ehs, pose_cond_fea=pose)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    t = sum(times) / len(times)
+    t = statistics.median(times)
     passes = frames * cfg_batch
-    return {"frames_per_s": 0.5 * passes / t, "s_per_sample": t, "cores": nthreads,
-            "sample": f"UNet forward on {passes} of the step's 48 frame-passes ({frames} frame(s) x {cfg_batch} CFG half) at the full 96x72 latent, "
-                      f"fp32, {nthreads} threads (fastest of a thread-count probe), denormals flushed, {len(times)} timed sample(s) of {t:.1f} s; "
-                      f"frames/s = ({passes} / 2) / t"}
+    # the step's windows overlap, so the clip's frames cost windows * fw * 2 passes per step
+    passes_per_step = 2 * cfg["fw"] * cfg["windows"]
+    fps = cfg["frames"] / (t * passes_per_step / passes)
+    return {"frames_per_s": fps, "s_per_sample": t, "cores": nthreads, "spread": (max(times) - min(times)) / t if len(times) > 1 else 0.0,
+            "sample": f"oracle UNet forward (fp32, {nthreads} threads pinned by rule, denormals flushed) on {passes} of the step's {passes_per_step} "
+                      f"frame-passes ({frames} frames x {cfg_batch} CFG halves) at the full {H}x{W} latent{' with the 16 reference banks' if cfg['banks'] else ''}; "
+                      f"median of {len(times)} timed samples after {warmup} warm-up: {t:.1f} s (min {min(times):.1f}, max {max(times):.1f}); "
+                      f"frames/s = {cfg['frames']} / (t * {passes_per_step} / {passes})"}
 
 
-def run_reference(args, rank):
+def workload_name(cfg, world):
+    banks = ", 16 reference K/V banks" if cfg["banks"] else ", no reference bank"
+    if cfg["name"] == "config5":
+        return (f"config5: 1 clip x 48 frames 576x1024 (latent 72x128), 3 context windows of 24 frames per timestep (context.py), CFG batch 2{banks}, "
+                f"random-init UNet3D 1.31B params" + (f"; the 6 (window x CFG-half) units split over {world} GPUs" if world > 1 else ""))
+    per = "1 clip/GPU" if world > 1 else "1 clip"
+    return f"{cfg['name']}: {per} x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D 1.31B params{banks}"
+
+
+def run_reference(args, rank, cfg):
     if rank != 0:
         return
-    r = cpu_reference_sample(max(1, min(args.steps, 2)), min(args.warmup, 1))
+    r = cpu_reference_sample(cfg, samples=max(1, min(args.steps, 3)), warmup=min(max(args.warmup, 0), 1))
     line = {"metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": r["frames_per_s"], "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 24 / r["frames_per_s"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "config2: 1 clip x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D 1.31B params, no reference bank",
-                       "note": "reference = oracle restatement of the reference PyTorch path on host CPU (diffusers not installable offline)"},
-            "cpu_baseline": {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * cfg["frames"] / r["frames_per_s"], "higher_is_better": True,
+            "scaling": "strong" if cfg["name"] == "config5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(cfg, 1),
+                       "note": "reference = oracle restatement of the reference PyTorch path on the host CPU (diffusers not installable offline); "
+                               "bounded sample scaled linearly in frame-passes"},
+            "cpu_baseline": {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                             "run_to_run_spread": r["spread"]},
             "e2e": {"value": r["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ native arm
-def run_native(args, rank, world, local_rank):
-    import ctypes as C
-
+def build_native(dev):
     import torch
 
     import humanvid_b200 as hv
-    from humanvid_b200 import _native as N
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
 
     unet = hv.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM, use_motion_module=True, use_inflated_groupnorm=True,
                                    motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True, motion_module_type="Vanilla",
@@ -210,67 +224,154 @@ def run_native(args, rank, world, local_rank):
     unet = unet.to(dev, torch.float16)
     synthetic_init_(unet, 7, dev)
     unet.refresh_native()
+    return unet
 
-    g = torch.Generator(device=dev).manual_seed(42 + rank)
+
+def time_oracle_eager(dev, x, ehs, pose, banks, native_ms, n=5):
+    """The library bar (SURVEY 6 / BASELINE.md 4): the reference-equivalent PyTorch path in fp16 eager (cuDNN / cuBLAS / SDPA of
+    torch 2.11) on the same B200, weights and inputs; CUDA-event median of n forwards after 2 warm-ups."""
+    import torch
+
+    from oracle import hv_oracle as O
+
+    ora = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval().to(dev, torch.float16)
+    synthetic_init_(ora, 7, dev)
+    if banks is not None:
+        O.set_reference_banks(ora, banks, cfg=True)
+    ts = []
+    with torch.no_grad():
+        for i in range(2 + n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = ora(x, torch.tensor(500, device=dev), ehs, pose_cond_fea=pose)[0]
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+    ok = bool(torch.isfinite(y).all())
+    del ora
+    torch.cuda.empty_cache()
+    ms = statistics.median(ts)
+    return {"ms_per_forward": ms, "min_ms": min(ts), "max_ms": max(ts), "samples": n, "finite": ok, "native_ms_per_forward": native_ms,
+            "native_speedup": ms / native_ms,
+            "how": "oracle/hv_oracle.py UNet3DConditionModel (the reference's modules restated with plain torch ops; F.scaled_dot_product_attention, "
+                   "nn.Conv2d, nn.Linear, nn.GroupNorm) in fp16 eager on the same GPU, same seeded weights and inputs as the native arm; CUDA events, "
+                   f"median of {n} after 2 warm-ups"}
+
+
+def run_native(args, rank, world, local_rank, cfg):
+    import ctypes as C
+
+    import torch
+
+    import humanvid_b200 as hv
+    from humanvid_b200 import _native as N
+    from humanvid_b200.device_loop import DeviceDenoiseLoop
+    from humanvid_b200.distributed import UnitExchange, gather_clip_latents, unit_list
+    from humanvid_b200.pipeline import uniform
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    is5 = cfg["name"] == "config5"
+    F, Fw, H, W = cfg["frames"], cfg["fw"], cfg["h"], cfg["w"]
+    unet = build_native(dev)
+    # config 5 is ONE clip (same data on every rank); configs 2-4 are one clip per rank (seed 42 + rank)
+    g = torch.Generator(device=dev).manual_seed(42 if is5 else 42 + rank)
     B = 2
-    sample = torch.randn(B, 4, F, H, W, generator=g, device=dev).half()
     ehs = torch.randn(B, 1, XDIM, generator=g, device=dev).half()
     ehs[:1] = 0
-    pose = (torch.randn(B, CH[0], F, H, W, generator=g, device=dev) * 0.5).half()
-    flops = FLOPS_CFG2
-    if args.banks:
+    banks = None
+    if cfg["banks"]:
         hv.ReferenceAttentionControl(unet, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
         lv = {320: H * W, 640: (H // 2) * (W // 2), 1280: (H // 4) * (W // 4)}
         names = {id(m): n for n, m in unet.named_modules()}
+        banks = []
         for blk in unet.reader_blocks():
             c = blk.norm1.normalized_shape[0]
             L = (H // 8) * (W // 8) if names[id(blk)].startswith("mid_block") else lv[c]
             blk.bank = [torch.randn(B, L, c, generator=g, device=dev).half()]
-        flops = FLOPS_CFG3
-
-    def step():
-        return unet(sample, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
+            banks.append(blk.bank[0])
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
-
             dist.barrier()
         torch.cuda.synchronize()
+
+    windows = list(uniform(0, 25, F, Fw, 1, 4))
+    assert len(windows) == cfg["windows"]
+    sample = torch.randn(B, 4, Fw, H, W, generator=g, device=dev).half()          # one window's CFG-doubled UNet input
+    poses = [(torch.randn(1, CH[0], Fw, H, W, generator=g, device=dev) * 0.5).half().repeat(2, 1, 1, 1, 1) for _ in windows]
+    loop = None
+    if is5:
+        latents = torch.randn(1, 4, F, H, W, generator=g, device=dev).half()
+        sched = hv.DDIMScheduler()
+        sched.set_timesteps(max(args.steps, args.warmup, 3) + 1)
+        kw = {}
+        if world > 1:
+            ex = UnitExchange(unit_list(len(windows), True))
+            kw = dict(exchange=ex, my_units=ex.my_units, all_units=ex.units)
+        loop = DeviceDenoiseLoop(unet, sched, latents, windows, ehs, poses, 3.5, True, **kw)
+        lat0 = loop.latents.clone()
+
+        def reset():
+            loop.latents.copy_(lat0)
+            loop.step_index.zero_()
+
+        def step():
+            loop._one_step()
+            return loop.latents
+    else:
+        def reset():
+            pass
+
+        def step():
+            return unet(sample, 500, ehs, pose_cond_fea=poses[0], return_dict=False)[0]
 
     for _ in range(max(args.warmup, 3)):
         out = step()
     torch.cuda.synchronize()
     if not torch.isfinite(out).all():
-        raise RuntimeError("non-finite UNet output")
-    launches = unet.last_launch_count
+        raise RuntimeError("non-finite output")
+    launches_fwd = unet.last_launch_count
+    n_fwd = (len(loop.my_units) if (is5 and world > 1) else len(windows)) if is5 else 1
+    launches_step = launches_fwd * n_fwd + ((n_fwd + 2) if is5 else 0)
 
-    # ---- kernel-only: inputs resident, K forwards bracketed by barrier + synchronize, device-timed
+    # ---- kernel-only: inputs resident, K steps bracketed by barrier + synchronize, device-timed
+    reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as cs:
         e0.record()
         for _ in range(args.steps):
             out = step()
-        if world > 1:
-            import torch.distributed as dist
-
-            gathered = torch.empty((world, *out.shape[1:]), device=dev, dtype=out.dtype)
-            dist.all_gather_into_tensor(gathered, out[1:2].contiguous())  # reassemble the clips' latents-sized predictions
+        if world > 1 and not is5:
+            gathered = gather_clip_latents(out[1:2].contiguous())   # config 4's single collective: reassemble the clips' latent-sized results
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1) / args.steps
     clocks = cs.summary()
 
-    # ---- end to end: the step's latents come from pinned host memory, the prediction goes back to the host
-    h_in = torch.empty(sample.shape, dtype=torch.float16).pin_memory()
-    h_in.copy_(sample.cpu())
+    # ---- end to end: the step's latents come from pinned host memory, the result goes back to the host
+    src = loop.latents if is5 else sample
+    h_in = torch.empty(src.shape, dtype=torch.float16).pin_memory()
+    h_in.copy_(lat0.cpu() if is5 else sample.cpu())
     h_out = torch.empty(out.shape, dtype=torch.float16).pin_memory()
+    reset()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        d_in = h_in.to(dev, non_blocking=True)
-        o = unet(d_in, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
+        if is5:
+            loop.latents.copy_(h_in, non_blocking=True)
+            o = step()
+        else:
+            d_in = h_in.to(dev, non_blocking=True)
+            o = unet(d_in, 500, ehs, pose_cond_fea=poses[0], return_dict=False)[0]
         h_out.copy_(o, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     barrier()
@@ -278,17 +379,26 @@ def run_native(args, rank, world, local_rank):
 
     t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
-        import torch.distributed as dist
-
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
-    # ---- per-operator device time of one more forward (events around every launch) -> roofline of the dominant kernel
+    # ---- per-operator device time of one more UNet forward (events around every launch) -> roofline of the dominant kernel
     lib = N.lib()
     lib.hv_set_profiling(unet._handle, 1)
-    step()
+    if is5:
+        loop.close()   # host timestep again
+    x1 = sample
+    if is5 and world > 1:   # a one-half unit, what this rank actually runs
+        unet._forward_flags = 4
+        unet(x1[1:], 500, ehs[1:], pose_cond_fea=poses[0][1:], return_dict=False)
+        unet._forward_flags = None
+    else:
+        unet(x1, 500, ehs, pose_cond_fea=poses[0], return_dict=False)
     cat_ms, cat_fl, cat_n = (C.c_double * 6)(), (C.c_double * 6)(), (C.c_int64 * 6)()
     N.check(lib.hv_get_profile(unet._handle, cat_ms, cat_fl, cat_n, 6), unet._handle)
     if os.environ.get("HV_TRACE"):
@@ -297,40 +407,62 @@ def run_native(args, rank, world, local_rank):
     names = ["tcgen05_gemm_linear", "tcgen05_implicit_gemm_conv3x3", "tcgen05_spatial_attention", "temporal_attention", "norms", "small_linear"]
     prof = {names[i]: {"ms": round(cat_ms[i], 3), "tflop": round(cat_fl[i] / 1e12, 3), "launches": int(cat_n[i]),
                        "tflops": round(cat_fl[i] / 1e9 / cat_ms[i], 1) if cat_ms[i] > 0 else None} for i in range(6)}
-    sustained, burst, hbm, src = peaks()
+    sustained, burst, hbm, src_pk = peaks()
     gemm_ms, gemm_fl = cat_ms[0] + cat_ms[1], cat_fl[0] + cat_fl[1]
     gemm_n = int(cat_n[0] + cat_n[1])
     achieved = gemm_fl / 1e9 / gemm_ms if gemm_ms > 0 else 0.0
+    executed_fl = sum(cat_fl[i] for i in range(6))   # counted by the runtime from the unpadded shapes of what it launched
 
-    cpu = cpu_reference_sample(1, 0) if not args.no_cpu_baseline else None
-    value = world * F / (ms / 1000.0)
+    # ---- the library bar: the oracle in fp16 eager on this GPU, same inputs (one UNet forward)
+    eager = None
+    if not args.no_eager:
+        torch.cuda.synchronize()
+        if not (is5 and world > 1):   # (the unit split has no single-GPU forward to compare with)
+            eager = time_oracle_eager(dev, sample, ehs, poses[0], banks, ms / len(windows) if is5 else ms)
+    cpu = cpu_reference_sample(cfg, samples=2 if args.quick_cpu else 3) if not args.no_cpu_baseline else None
+
+    frames_total = F if is5 else world * F
+    flops_step = cfg["tflop_fwd"] * 1e12 * (len(windows) if is5 else world)
+    skipped_fwd = 2.07 * (H * W) / (96 * 72)   # attn2 to_q / to_out scale with the token count
+    exec_step = flops_step * (1.0 - skipped_fwd / cfg["tflop_fwd"])
+    value = frames_total / (ms / 1000.0)
+    traffic = measured_traffic()
     line = {
         "metric": "denoising-UNet frames/sec, 24x768x576, CFG", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic", "impl": "native",
-        "config": {"workload": ("config3" if args.banks else "config2") + ": 1 clip/GPU x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D "
-                   "1.31B params" + (", 16 reference K/V banks" if args.banks else ", no reference bank"),
-                   "global_batch_clips": world, "parallelism": f"clip-per-gpu x{world}" + (", final all_gather of predictions" if world > 1 else ""),
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if is5 else "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "impl": "native",
+        "config": {"workload": workload_name(cfg, world), "global_batch_clips": 1 if is5 else world,
+                   "parallelism": (f"(window x CFG-half) units over {world} ranks, one all_gather of unit predictions per step" if (is5 and world > 1)
+                                   else f"clip-per-gpu x{world}" + (", final all_gather of predictions" if world > 1 else "")),
                    "l2": "working set per step (2.6 GB weights + multi-GB activations) >> 126 MB L2, no flush needed",
                    "cond_features": "pose_cond_fea resident (step-invariant; hoisted out of the step as the pipeline's feature cache does)"},
-        "tflops_per_step": flops / 1e12, "achieved_tflops": world and flops / 1e9 / ms,
-        "frac_of_tensor_roofline_sustained": flops / 1e9 / ms / sustained,
-        "e2e": {"value": world * F / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 2),
-                "d2h_bytes_per_step": int(h_out.numel() * 2), "api": "humanvid_b200.UNet3DConditionModel.forward (host latents -> host prediction)"},
-        "gpu_launches": int(launches) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<128|256> (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved, "peak": sustained,
-                     "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})",
-                     "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_tflop_per_step": gemm_fl / 1e12,
-                     "traffic": None},
+        "tflops_per_step": flops_step / 1e12, "executed_tflops_per_step": exec_step / 1e12,
+        "achieved_tflops": exec_step / 1e9 / ms, "frac_of_tensor_roofline_sustained": exec_step / 1e9 / ms / sustained / world,
+        "flops_note": "algorithmic FLOPs per step from SURVEY 8d; `executed` drops attn2's to_q/to_out over all tokens (2.07 TF per forward), which the "
+                      "one-key cross-attention collapse never runs; achieved_tflops and the roofline fraction are on EXECUTED FLOPs",
+        "e2e": {"value": frames_total / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 2),
+                "d2h_bytes_per_step": int(h_out.numel() * 2),
+                "api": ("humanvid_b200.device_loop.DeviceDenoiseLoop step (host latents -> 3 window forwards + glue -> host latents)" if is5 else
+                        "humanvid_b200.UNet3DConditionModel.forward (host latents -> host prediction)")},
+        "gpu_launches": int(launches_step) * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<128|160|256> (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src_pk})",
+                     "launches_per_forward": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_tflop_per_forward": gemm_fl / 1e12,
+                     "traffic": (traffic or {}).get("gemm_kernel_avg_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "executed_tflop_per_forward_all_kernels": executed_fl / 1e12},
         "op_profile": prof,
         "clocks": clocks,
     }
+    if eager is not None:
+        eager["value"] = frames_total / (eager["ms_per_forward"] * (len(windows) if is5 else 1) / 1000.0)
+        eager["unit"] = "frames/s"
+        line["oracle_gpu_eager"] = eager
     if cpu is not None:
-        line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+        line["cpu_baseline"] = {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"],
+                                "run_to_run_spread": cpu["spread"]}
     print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -340,21 +472,33 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--banks", type=int, default=0, help="1 = config 3 (reference K/V banks on)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5], help="BASELINE config; default 2 on one GPU, 4 (= N x config 3) on N > 1")
+    ap.add_argument("--banks", type=int, default=0, help="legacy: 1 = config 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the fp16-eager oracle timing on the GPU")
+    ap.add_argument("--quick-cpu", action="store_true", help="2 instead of 3 timed CPU samples")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = max(world, args.gpus)
+    c = args.config or (3 if args.banks else (4 if n > 1 else 2))
+    if c == 4 and n == 1:
+        c = 3
+    if c in (2, 3) and n > 1:
+        c = 4 if c == 3 else 2   # N > 1 with --config 2 keeps banks off (the round-1 scaling workload)
+    cfg = dict(CONFIGS[c])
+    if c == 2 and n > 1:
+        cfg["name"] = "config2 per GPU"
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, cfg)
         return
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29533"), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_native(args, rank, world, local_rank)
+    run_native(args, rank, world, local_rank, cfg)
 
 
 if __name__ == "__main__":

@@ -1245,10 +1245,18 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
       float* sm = gmax + (j & 1) * 256;
       sm[hf * 128 + r] = fmaxf(mx0, mx1) * sc;
-      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (PE == 17) {
+        // the row max is exchanged between exactly two warps (the two column halves of one TMEM lane quadrant): a 64-thread named
+        // barrier per warp pair instead of one 256-thread barrier per group lets the pairs drift apart
+        asm volatile("bar.sync %0, 64;" ::"r"(5 + g * 4 + qd) : "memory");
+      } else if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
       const float rowmax = fmaxf(sm[r], sm[128 + r]);
-      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
+      // PE == 16: the exponentials run as ex2.approx.f16x2 (two per MUFU op) on arguments rounded to fp16, whose absolute error grows
+      // with |s - m|: keep the stale-max excess below 2 (half-ulp 2^-11 -> 3.4e-4 on the largest probabilities, the size of their own
+      // fp16 rounding) instead of 8
+      constexpr float kThr = PE == 16 ? 2.0f : kRescaleThreshold;
+      const bool grow = rowmax > m_used + kThr;   // identical in both threads of the row
       const float m_new = grow ? rowmax : m_used;
       tick(2);
       tmem_ld_wait();
@@ -1287,7 +1295,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a0 = fmaf(__uint_as_float(raw[2 * i]), sc, -m_used), a1 = fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used);
-            if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
+            if (PE == 16) pk[i] = ex2_h2(pack_h2(a0, a1));   // one MUFU op -> two probabilities, already packed fp16
+            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
             else pk[i] = pack_h2(fast_exp2(a0), fast_exp2(a1));
           }
         } else {
@@ -1456,7 +1465,7 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   static int use_pt = 1;    // HV_ATTN_PT=0: keep P in shared memory even where it fits in TMEM
   if (!attr) {
     if (const char* pv = getenv("HV_ATTN_POLY")) mode = atoi(pv);
-    if (mode != 0 && mode != 2 && mode != 4 && mode != 13 && mode != 31) mode = 0;
+    if (mode != 0 && mode != 2 && mode != 4 && mode != 13 && mode != 16 && mode != 17 && mode != 31) mode = 0;
     if (const char* pt = getenv("HV_ATTN_PT")) use_pt = atoi(pt);
     const char* ev = getenv("HV_ATTN_WARPS");
     if (ev) nwarps = atoi(ev);
@@ -1493,9 +1502,11 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
   }
   static const int pp_mode = [] { const char* v = getenv("HV_ATTN_PP"); return v ? atoi(v) : 2; }();  // 0 off, 1 token hand-off, 2 free-running groups (default: ~8 % fewer clocks than attn_kernel8 in the network)
-  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 4 || mode == 31)) {
+  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 4 || mode == 16 || mode == 17 || mode == 31)) {
     if (mode == 31) return pp_mode == 2 ? launch_attn_pp<D, 31, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
                                         : launch_attn_pp<D, 31, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mode == 16) return launch_attn_pp<D, 16, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mode == 17) return launch_attn_pp<D, 17, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (pp_mode == 2) return launch_attn_pp<D, 0, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (mode == 4) return launch_attn_pp<D, 4, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (mode == 2) return launch_attn_pp<D, 2, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);

@@ -105,7 +105,7 @@ int hv_op_small_linear(const void* X, const void* W, const void* bias, void* out
   CK(launch_small_linear(H(X), H(W), H(bias), HM(out), (int)M, (int)N, (int)K, act_in, ST(stream)), "hv_op_small_linear");
 }
 int hv_op_timestep_embedding(int64_t timestep, void* out, int64_t B, int64_t dim, hv_stream_t stream) {
-  CK(launch_timestep_embedding(timestep, HM(out), (int)B, (int)dim, ST(stream)), "hv_op_timestep_embedding");
+  CK(launch_timestep_embedding(timestep, nullptr, nullptr, HM(out), (int)B, (int)dim, ST(stream)), "hv_op_timestep_embedding");
 }
 int hv_pack_conv3x3(const void* W, void* out, int64_t Cout, int64_t Cin, int64_t Cout_pad, int64_t Cin_pad, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;
@@ -118,6 +118,33 @@ int hv_pack_geglu(const void* W, void* out, int64_t rows, int64_t K, hv_stream_t
 int hv_pack_heads(const void* W, void* out, int32_t heads, int32_t d, int32_t dpad, int64_t K, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;
   CK(launch_pack_heads(H(W), HM(out), heads, d, dpad, (int)K, device_sms(), ST(stream)), "hv_pack_heads");
+}
+int hv_op_window_gather(const void* latents, const int32_t* frame_idx, void* out, int64_t Bl, int64_t C, int64_t Ftot, int64_t Fw, int64_t HW,
+                        int32_t repeat, hv_stream_t stream) {
+  if (!device_sms()) return HV_ERR_CUDA;
+  if (!latents || !frame_idx || !out || Bl <= 0 || C <= 0 || Ftot <= 0 || Fw <= 0 || HW <= 0 || repeat < 1) { set_error("hv_op_window_gather: bad argument"); return HV_ERR_INVALID; }
+  CK(launch_window_gather(H(latents), frame_idx, HM(out), (int)Bl, (int)C, (int)Ftot, (int)Fw, (int)HW, repeat, device_sms(), ST(stream)), "hv_op_window_gather");
+}
+int hv_op_cfg_ddim_step(const void* const* pred_uncond, const void* const* pred_cond, int32_t n_windows, const int32_t* inv, int32_t K,
+                        const float* coef, const int32_t* step_index, void* latents, int64_t Bl, int64_t C, int64_t Ftot, int64_t Fw, int64_t HW,
+                        float guidance_scale, int32_t prediction_type, hv_stream_t stream) {
+  if (!device_sms()) return HV_ERR_CUDA;
+  if (!pred_uncond || !inv || !coef || !latents || n_windows < 1 || n_windows > kMaxWindows || K < 1 || (prediction_type != 0 && prediction_type != 1)) {
+    set_error("hv_op_cfg_ddim_step: bad argument (1..%d windows, prediction_type 0 = v_prediction / 1 = epsilon)", kMaxWindows);
+    return HV_ERR_INVALID;
+  }
+  StepPreds sp{};
+  for (int w = 0; w < n_windows; ++w) {
+    sp.uncond[w] = H(pred_uncond[w]);
+    sp.cond[w] = pred_cond ? H(pred_cond[w]) : nullptr;
+    if (!sp.uncond[w] || (pred_cond && !sp.cond[w])) { set_error("hv_op_cfg_ddim_step: window %d has a NULL prediction", w); return HV_ERR_INVALID; }
+  }
+  CK(launch_cfg_ddim_step(sp, inv, K, coef, step_index, HM(latents), (int)Bl, (int)C, (int)Ftot, (int)Fw, (int)HW, guidance_scale, pred_cond ? 1 : 0,
+                          prediction_type, device_sms(), ST(stream)), "hv_op_cfg_ddim_step");
+}
+int hv_op_advance_index(int32_t* index, hv_stream_t stream) {
+  if (!index) return HV_ERR_INVALID;
+  CK(launch_advance_index(index, ST(stream)), "hv_op_advance_index");
 }
 int hv_dbg_gemm(const void* A, int64_t lda, const void* W, float* out, int64_t M, int64_t N, int64_t K, hv_stream_t stream) {
   CK(launch_dbg_gemm(H(A), lda, H(W), out, (int)M, (int)N, (int)K, ST(stream)), "hv_dbg_gemm");

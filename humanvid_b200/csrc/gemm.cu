@@ -9,7 +9,7 @@
 //                               double-buffered in TMEM (2 x BLOCK_N columns); owns TMEM alloc/dealloc
 //   warps 2..17 epilogue      : tcgen05.ld of the accumulator (one output row per thread, four warps per TMEM lane
 //                               quadrant splitting the columns), bias / time-embedding row vector / activation /
-//                               GEGLU / residual, fp16 store
+//                               GEGLU / residual in fp32, one fp16 rounding at the store
 // The A operand is addressed through TMA only, so a 3x3 convolution over a channels-last (N,H,W,C) tensor is the
 // same kernel: k-block kb = (tap, 64-channel block) and the tile of 128 output pixels is a (bn x bh x bw) box whose
 // input window is fetched with the box shifted by the tap offset; TMA's out-of-bounds zero fill is the padding.
@@ -101,10 +101,6 @@ __device__ __forceinline__ void ldsf8(const float* src, float* v) {  // shared m
   const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
-  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ void load8(const __half* src, float* v) {
   uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
@@ -367,56 +363,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             for (int g = 0; g < 2; ++g) {
               const int col = colbase + c * 16 + g * 8;
               if (c * 16 + g * 8 < SL && col < e.n_valid) {
+                // fp32 all the way: accumulator + bias (+ time-embedding row vector) -> activation -> + residual, ONE rounding
+                // at the store (the fp32 oracle is the parity anchor; the reference's eager fp16 path rounds after every op)
                 float v[8], t[8];
-                if (lean) {
-                  // bias -> fp16 (the linear's own output rounding) -> + residual in packed half arithmetic -> box
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]);
-                  if (has_bias) {
-                    ldsf8(sbias + c * 16 + g * 8, t);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += t[i];
-                  }
-                  uint4 o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                  uint4* sp4 = reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4));
-                  if (has_res) {
-                    const uint4 rr = *sp4;
-                    o.x = hadd2_u32(o.x, rr.x);
-                    o.y = hadd2_u32(o.y, rr.y);
-                    o.z = hadd2_u32(o.z, rr.z);
-                    o.w = hadd2_u32(o.w, rr.w);
-                  }
-                  *sp4 = o;
-                  continue;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]) + rowbias;
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c & 1][g * 8 + i]);
                 if (has_bias) {
                   ldsf8(sbias + c * 16 + g * 8, t);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] += t[i];
                 }
+                if (!lean) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
-                if (rv != nullptr) {
-                  load8(rv + col, t);
+                  for (int i = 0; i < 8; ++i) v[i] += rowbias;
+                  if (rv != nullptr) {
+                    load8(rv + col, t);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+                    for (int i = 0; i < 8; ++i) v[i] += t[i];
+                  }
+                  if (e.act == ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                  } else if (e.act == ACT_SILU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+                  }
                 }
-                if (e.act == ACT_RELU) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                } else if (e.act == ACT_SILU) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
-                }
-                __half* sp = reinterpret_cast<__half*>(myrow + (((2 * c + g) ^ swz) << 4));
+                uint4* sp4 = reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4));
                 if (has_res) {
-                  lds8(sp, t);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] += t[i];
+                  const uint4 rr = *sp4;
+                  add_h2(v[0], v[1], rr.x);
+                  add_h2(v[2], v[3], rr.y);
+                  add_h2(v[4], v[5], rr.z);
+                  add_h2(v[6], v[7], rr.w);
                 }
-                store8(sp, v);
+                *sp4 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
               }
             }
           }
@@ -447,14 +428,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               }
               uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __half2 h2 = __floats2half2_rn(__uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i],
-                                                     __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1]);
-                const float2 gf = __half22float2(__floats2half2_rn(__uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i],
-                                                                   __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1]));
-                const __half2 ge = __floats2half2_rn(gelu_erf_fast(gf.x), gelu_erf_fast(gf.y));
-                const __half2 pr = __hmul2(h2, ge);
-                o[i] = *reinterpret_cast<const uint32_t*>(&pr);
+              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32, one rounding at the store
+                const float h0 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i], h1 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1];
+                const float g0 = __uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i], g1 = __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1];
+                o[i] = pack_h2(h0 * gelu_erf_fast(g0), h1 * gelu_erf_fast(g1));
               }
               *reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -544,28 +521,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] += t[i];
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = r16(v[i]);
                 if (rv != nullptr) {
                   load8(rv + col, t);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = r16(v[i] + t[i]);
+                  for (int i = 0; i < 8; ++i) v[i] += t[i];
                 }
                 if (e.act == ACT_RELU) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 } else if (e.act == ACT_SILU) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = r16(silu_f(v[i]));
+                  for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
                 }
                 if (res != nullptr) {
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&rres[c & 1][g]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(h2[i]);
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
-                  }
+                  const uint4 rr = rres[c & 1][g];
+                  add_h2(v[0], v[1], rr.x);
+                  add_h2(v[2], v[3], rr.y);
+                  add_h2(v[4], v[5], rr.z);
+                  add_h2(v[6], v[7], rr.w);
                 }
                 if (row_ok) store8(out + col, v);
               }
@@ -573,8 +546,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           }
         } else {
           // GEGLU (BLOCK_N == 256): tile columns [0,128) are "hidden", [128,256) the matching "gate" rows of the packed
-          // weight; this warp owns hidden columns [cs*32, cs*32+32) and their gates.  The fp16 roundings of the reference's
-          // eager path (proj output, gelu output, product) are reproduced with packed-half arithmetic.
+          // weight; this warp owns hidden columns [cs*32, cs*32+32) and their gates.
           constexpr int NC = (BLOCK_N / 8) / 16;
           const int hcol0 = cs * (BLOCK_N / 8);
           uint32_t hraw[2][16], graw[2][16];
@@ -600,14 +572,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               }
               uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __half2 h2 = __floats2half2_rn(__uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i],
-                                                     __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1]);
-                const float2 gf = __half22float2(__floats2half2_rn(__uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i],
-                                                                   __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1]));
-                const __half2 ge = __floats2half2_rn(gelu_erf_fast(gf.x), gelu_erf_fast(gf.y));
-                const __half2 pr = __hmul2(h2, ge);
-                o[i] = *reinterpret_cast<const uint32_t*>(&pr);
+              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32, one rounding at the store
+                const float h0 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i], h1 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1];
+                const float g0 = __uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i], g1 = __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1];
+                o[i] = pack_h2(h0 * gelu_erf_fast(g0), h1 * gelu_erf_fast(g1));
               }
               if (row_ok && ocol < e.n_valid) *reinterpret_cast<uint4*>(out + ocol) = make_uint4(o[0], o[1], o[2], o[3]);
             }

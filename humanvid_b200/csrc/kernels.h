@@ -32,7 +32,7 @@ cudaError_t launch_add(const __half* a, const __half* b, __half* out, long long 
 cudaError_t launch_pixel_unshuffle(const __half* x, __half* out, int B, int C, int F, int H, int W, int r, int num_sms, cudaStream_t s);
 cudaError_t launch_small_linear(const __half* x, const __half* w, const __half* bias, __half* out, int M, int N, int K, int act_in,
                                 cudaStream_t s);
-cudaError_t launch_timestep_embedding(long long timestep, __half* out, int B, int dim, cudaStream_t s);
+cudaError_t launch_timestep_embedding(long long timestep, const long long* table, const int* index, __half* out, int B, int dim, cudaStream_t s);
 cudaError_t launch_conv3x3_direct(const __half* x, const __half* w, const __half* bias, __half* out, long long NF, int H, int W, int Cin,
                                   int Cout, int stride, int act, const __half* add, int num_sms, cudaStream_t s);
 cudaError_t launch_pack_conv3x3(const __half* w, __half* out, int Cout, int Cin, int Cout_pad, int Cin_pad, int num_sms, cudaStream_t s);
@@ -40,6 +40,18 @@ cudaError_t launch_conv3x3_direct_padded(const __half* x, const __half* w, const
                                          int Cin, int Cout, int ldo, int act, int num_sms, cudaStream_t s);
 cudaError_t launch_pack_geglu(const __half* w, __half* out, int rows, int K, int num_sms, cudaStream_t s);
 cudaError_t launch_pack_heads(const __half* w, __half* out, int heads, int d, int dpad, int K, int num_sms, cudaStream_t s);
+// ---- per-timestep glue of the denoising loop (step.cu)
+constexpr int kMaxWindows = 32;
+struct StepPreds {                       // window w's UNet prediction, (Bl, C, Fw, HW) fp16 each; cond unused without CFG
+  const __half* uncond[kMaxWindows];
+  const __half* cond[kMaxWindows];
+};
+cudaError_t launch_window_gather(const __half* latents, const int* idx, __half* out, int Bl, int C, int Ftot, int Fw, int HW, int R, int num_sms,
+                                 cudaStream_t s);
+cudaError_t launch_cfg_ddim_step(const StepPreds& preds, const int* inv, int K, const float* coef, const int* step_idx, __half* latents, int Bl, int C,
+                                 int Ftot, int Fw, int HW, float guidance, int cfg, int epsilon, int num_sms, cudaStream_t s);
+cudaError_t launch_advance_index(int* idx, cudaStream_t s);
+
 cudaError_t launch_dbg_gemm(const __half* a, long long lda, const __half* w, float* out, int M, int N, int K, cudaStream_t s);
 
 }  // namespace hv

@@ -92,7 +92,7 @@ __global__ void pixel_unshuffle_kernel(const __half* __restrict__ x, __half* __r
   }
 }
 
-// y[m][n] = r16( sum_k act(x[m][k]) * w[n][k] + bias[n] ); one warp per output element (M is tiny).
+// y[m][n] = fp16( sum_k act(x[m][k]) * w[n][k] + bias[n] ); one warp per output element (M is tiny).
 __global__ void small_linear_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                                     __half* __restrict__ out, int M, int N, int K, int act_in) {
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -104,8 +104,8 @@ __global__ void small_linear_kernel(const __half* __restrict__ x, const __half* 
     float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + static_cast<long long>(m) * K + k));
     float2 wv = __half22float2(*reinterpret_cast<const __half2*>(w + static_cast<long long>(n) * K + k));
     if (act_in == 2) {
-      xv.x = r16(silu_f(xv.x));
-      xv.y = r16(silu_f(xv.y));
+      xv.x = silu_f(xv.x);
+      xv.y = silu_f(xv.y);
     }
     acc += xv.x * wv.x + xv.y * wv.y;
   }
@@ -114,7 +114,9 @@ __global__ void small_linear_kernel(const __half* __restrict__ x, const __half* 
   if (lane == 0) out[static_cast<long long>(m) * N + n] = __float2half_rn(acc + (bias ? __half2float(bias[n]) : 0.f));
 }
 
-__global__ void timestep_embedding_kernel(float t, __half* __restrict__ out, int B, int dim) {
+__global__ void timestep_embedding_kernel(float t, const long long* __restrict__ table, const int* __restrict__ index,
+                                          __half* __restrict__ out, int B, int dim) {
+  if (table != nullptr) t = static_cast<float>(table[*index]);   // device-resident timestep (graph replay of a denoising loop)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= B * half) return;
@@ -165,8 +167,8 @@ __global__ void conv3x3_direct_kernel(const __half* __restrict__ x, const __half
     for (int j = 0; j < 8; ++j) {
       const int co = cg * 8 + j;
       if (co < Cout) {
-        float v = r16(acc[j] + (bias ? __half2float(bias[co]) : 0.f));
-        if (act == 2) v = r16(silu_f(v));
+        float v = acc[j] + (bias ? __half2float(bias[co]) : 0.f);
+        if (act == 2) v = silu_f(v);
         else if (act == 1) v = fmaxf(v, 0.f);
         if (add) v = v + __half2float(add[obase + co]);
         out[obase + co] = __float2half_rn(v);
@@ -264,9 +266,9 @@ cudaError_t launch_small_linear(const __half* x, const __half* w, const __half* 
   small_linear_kernel<<<static_cast<unsigned>((warps * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(x, w, bias, out, M, N, K, act_in);
   HV_LAUNCH_CHECK();
 }
-cudaError_t launch_timestep_embedding(long long timestep, __half* out, int B, int dim, cudaStream_t s) {
+cudaError_t launch_timestep_embedding(long long timestep, const long long* table, const int* index, __half* out, int B, int dim, cudaStream_t s) {
   const int n = B * dim / 2;
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<float>(timestep), out, B, dim);
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<float>(timestep), table, index, out, B, dim);
   HV_LAUNCH_CHECK();
 }
 cudaError_t launch_conv3x3_direct(const __half* x, const __half* w, const __half* bias, __half* out, long long NF, int H, int W, int Cin,

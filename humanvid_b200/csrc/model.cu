@@ -172,6 +172,21 @@ struct hv_model {
   void* private_ws = nullptr;
   size_t private_ws_bytes = 0;
   int64_t launches = 0;
+  // device-resident timestep (CUDA-graph replay of a denoising loop): t = ts_table[*ts_index] when set
+  const long long* ts_table = nullptr;
+  const int* ts_index = nullptr;
+  // debug taps (error ladder): the activation leaving block i of the forward is copied to tap_dst[i] (channels-last fp16)
+  struct TapInfo { std::string name; int NF, H, W, C; };
+  std::vector<TapInfo> tap_list;
+  std::vector<void*> tap_dst;
+  void tap(const std::string& name, const Tens& t) {
+    const size_t i = tap_list.size();
+    tap_list.push_back({name, t.NF, t.H, t.W, t.C});
+    if (!ar.dry && i < tap_dst.size() && tap_dst[i] != nullptr) {
+      launches += 1;
+      ck(cudaMemcpyAsync(tap_dst[i], t.p, static_cast<size_t>(t.numel()) * 2, cudaMemcpyDeviceToDevice, st), "tap copy");
+    }
+  }
   // optional per-category device timing (bench.py's roofline): events bracket every operator launch
   enum Cat { CAT_GEMM = 0, CAT_CONV = 1, CAT_ATTN = 2, CAT_TATTN = 3, CAT_NORM = 4, CAT_MISC = 5, CAT_N = 6 };
   bool profiling = false;
@@ -596,7 +611,7 @@ struct hv_model {
   }
 
   // Transformer3DModel + TemporalBasicTransformerBlock (+ reference-bank read hook)
-  Tens spatial_fwd(const SpatialW& w, const Tens& x, const __half* ehs, int B, int F, bool cfg_split) {
+  Tens spatial_fwd(const SpatialW& w, const Tens& x, const __half* ehs, int B, int F, uint32_t flags) {
     Tens out = alloc_act(x.NF, x.H, x.W, x.C);
     Scope s(ar);
     const int C = w.C, L = x.H * x.W;
@@ -625,21 +640,32 @@ struct hv_model {
         launches += 1;
         ck(cudaMemcpyAsync(bank_out[w.reader_idx], n1.p, static_cast<size_t>(tokens) * C * 2, cudaMemcpyDeviceToDevice, st), "bank write");
       }
-      const bool use_bank = w.bank != nullptr && bank_out == nullptr;
+      // HV_FLAG_CFG: batch = [uncond ; cond], the first half ignores the bank.  HV_FLAG_UNCOND_ONLY / HV_FLAG_COND_ONLY: the batch
+      // holds one CFG half only (a (window x CFG-half) unit of a multi-GPU split); a cond-only batch of B items reads the LAST B
+      // items of the bank (the bank is written for [uncond ; cond]).
+      const bool cfg_split = (flags & HV_FLAG_CFG) != 0 && B >= 2 && B % 2 == 0 && !(flags & (HV_FLAG_UNCOND_ONLY | HV_FLAG_COND_ONLY));
+      const bool use_bank = w.bank != nullptr && bank_out == nullptr && !(flags & HV_FLAG_UNCOND_ONLY);
       __half *kb = nullptr, *vbt = nullptr;
       int64_t ldvbt = 0, Lbp = 0;
       if (use_bank) {
-        if (w.bank_B != B) fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld, forward batch is %d", w.name.c_str(), (long long)w.bank_B, B);
-        const int64_t bt = w.bank_B * w.bank_L;
+        int64_t item0 = 0;
+        if (flags & HV_FLAG_COND_ONLY) {
+          if (w.bank_B < B) fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld < forward batch %d", w.name.c_str(), (long long)w.bank_B, B);
+          item0 = w.bank_B - B;
+        } else if (w.bank_B != B) {
+          fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld, forward batch is %d", w.name.c_str(), (long long)w.bank_B, B);
+        }
+        const __half* bank = w.bank + item0 * w.bank_L * C;
+        const int64_t bt = static_cast<int64_t>(B) * w.bank_L;
         kb = alloc_h(bt * hp);
-        gemm(w.bank, C, nullptr, 0, 0, w.wk, kb, hp, bt, nullptr);
+        gemm(bank, C, nullptr, 0, 0, w.wk, kb, hp, bt, nullptr);
         Lbp = rup(w.bank_L, 8);
-        ldvbt = w.bank_B * Lbp;
+        ldvbt = static_cast<int64_t>(B) * Lbp;
         vbt = alloc_h(vrows * ldvbt);
         if (!ar.dry) {
           launches += 1;
           Timed tm(this, CAT_GEMM, 2.0 * bt * C * C);
-          ckop(op_gemm_batched_b(w.wv.p, C, w.bank, C, vbt, ldvbt, vrows, w.bank_B, w.bank_L, Lbp, C, w.vones, st), "bank V^T gemm");
+          ckop(op_gemm_batched_b(w.wv.p, C, bank, C, vbt, ldvbt, vrows, B, w.bank_L, Lbp, C, w.vones, st), "bank V^T gemm");
         }
       }
       Tens o = alloc_act(x.NF, x.H, x.W, C);
@@ -728,6 +754,7 @@ struct hv_model {
     ar.off = 0;
     ar.peak = 0;
     launches = 0;
+    tap_list.clear();
     if (!dry) { recs.clear(); ev_used = 0; }
     if (dry) {
       ar.base = nullptr;
@@ -743,10 +770,9 @@ struct hv_model {
     const int* ch = cfg.block_out_channels;
     const int NF = B * F;
     if ((H % 8) || (W % 8)) fail(HV_ERR_INVALID, "latent size %dx%d must be a multiple of 8 (three stride-2 levels)", H, W);
-    const bool cfg_split = (flags & HV_FLAG_CFG) != 0 && B >= 2 && B % 2 == 0;
     // time embedding (unet_3d.py:446-467)
     __half* tsin = alloc_h(static_cast<int64_t>(B) * ch[0]);
-    if (!ar.dry) { launches += 1; ck(launch_timestep_embedding(timestep, tsin, B, ch[0], st), "timestep embedding"); }
+    if (!ar.dry) { launches += 1; ck(launch_timestep_embedding(timestep, ts_table, ts_index, tsin, B, ch[0], st), "timestep embedding"); }
     __half* e1 = op_small_linear(tsin, te1, B, HV_ACT_NONE);
     __half* emb = op_small_linear(e1, te2, B, HV_ACT_SILU);
     // conv_in (+ pose_cond_fea as the epilogue residual); the 4 latent channels are zero-padded to one 64-wide k-block
@@ -759,37 +785,47 @@ struct hv_model {
       if (pose) ck(launch_ncfhw_to_nhwc(pose, pc.p, B, ch[0], F, H, W, 0, st), "pose layout");
     }
     Tens h = op_conv3(x0, conv_in, 1, nullptr, 1, HV_ACT_NONE, pose ? &pc : nullptr);
+    tap("conv_in", h);
     std::vector<Tens> skips{h};
     for (size_t i = 0; i < down.size(); ++i) {
       auto& d = down[i];
+      const std::string pb = "down_blocks." + std::to_string(i);
       for (size_t j = 0; j < d.res.size(); ++j) {
         h = resnet_fwd(d.res[j], h, nullptr, emb, B, F);
-        if (!d.attn.empty()) h = spatial_fwd(d.attn[j], h, ehs, B, F, cfg_split);
-        if (!d.mm.empty()) h = motion_fwd(d.mm[j], h, B, F);
+        tap(pb + ".resnets." + std::to_string(j), h);
+        if (!d.attn.empty()) { h = spatial_fwd(d.attn[j], h, ehs, B, F, flags); tap(pb + ".attentions." + std::to_string(j), h); }
+        if (!d.mm.empty()) { h = motion_fwd(d.mm[j], h, B, F); tap(pb + ".motion_modules." + std::to_string(j), h); }
         skips.push_back(h);
       }
       if (d.has_down) {
         h = op_conv3(h, d.down, 2, nullptr, 1, HV_ACT_NONE, nullptr);
+        tap(pb + ".downsamplers.0", h);
         skips.push_back(h);
       }
     }
     h = resnet_fwd(mid.res[0], h, nullptr, emb, B, F);
-    h = spatial_fwd(mid.attn[0], h, ehs, B, F, cfg_split);
-    if (!mid.mm.empty()) h = motion_fwd(mid.mm[0], h, B, F);
+    tap("mid_block.resnets.0", h);
+    h = spatial_fwd(mid.attn[0], h, ehs, B, F, flags);
+    tap("mid_block.attentions.0", h);
+    if (!mid.mm.empty()) { h = motion_fwd(mid.mm[0], h, B, F); tap("mid_block.motion_modules.0", h); }
     h = resnet_fwd(mid.res[1], h, nullptr, emb, B, F);
+    tap("mid_block.resnets.1", h);
     for (size_t i = 0; i < up.size(); ++i) {
       auto& u = up[i];
+      const std::string pb = "up_blocks." + std::to_string(i);
       for (size_t j = 0; j < u.res.size(); ++j) {
         Tens skip = skips.back();
         skips.pop_back();
         h = resnet_fwd(u.res[j], h, &skip, emb, B, F);
-        if (!u.attn.empty()) h = spatial_fwd(u.attn[j], h, ehs, B, F, cfg_split);
-        if (!u.mm.empty()) h = motion_fwd(u.mm[j], h, B, F);
+        tap(pb + ".resnets." + std::to_string(j), h);
+        if (!u.attn.empty()) { h = spatial_fwd(u.attn[j], h, ehs, B, F, flags); tap(pb + ".attentions." + std::to_string(j), h); }
+        if (!u.mm.empty()) { h = motion_fwd(u.mm[j], h, B, F); tap(pb + ".motion_modules." + std::to_string(j), h); }
       }
       if (u.has_up) {
         Tens big = alloc_act(h.NF, 2 * h.H, 2 * h.W, h.C);
         if (!ar.dry) { launches += 1; ck(launch_upsample2x(h.p, big.p, h.NF, h.H, h.W, h.C, sms, st), "upsample"); }
         h = op_conv3(big, u.up, 1, nullptr, 1, HV_ACT_NONE, nullptr);
+        tap(pb + ".upsamplers.0", h);
       }
     }
     if (cfg.kind == HV_KIND_UNET2D_REF) {   // no post-process: the forward's value is the last up block's output (B, C0, h, w)
@@ -859,18 +895,16 @@ struct hv_model {
     return HV_ERR_INVALID;                                \
   }
 
+// The forwards never allocate: a caller that passes no workspace must have called hv_reserve_workspace for a shape at least as
+// large (cudaMalloc synchronises the device and is illegal under stream capture).
 static void* get_ws(hv_model* m, void* ws, size_t ws_bytes, size_t need, size_t* have) {
   if (ws) {
     *have = ws_bytes;
     return ws;
   }
-  if (m->private_ws_bytes < need) {
-    if (m->private_ws) cudaFree(m->private_ws);
-    m->private_ws = nullptr;
-    m->private_ws_bytes = 0;
-    ck(cudaMalloc(&m->private_ws, need), "cudaMalloc(workspace)");
-    m->private_ws_bytes = need;
-  }
+  if (m->private_ws_bytes < need)
+    fail(HV_ERR_STATE, "workspace == NULL and the handle's reserved workspace (%zu bytes) is smaller than the %zu this shape needs: call hv_reserve_workspace first",
+         m->private_ws_bytes, need);
   *have = m->private_ws_bytes;
   return m->private_ws;
 }
@@ -1027,6 +1061,53 @@ static size_t measure(hv_model* h, int B, int F, int H, int W) {
     h->camera_forward(nullptr, nullptr, B, F, H, W);
   }
   return h->ar.peak + 4096;
+}
+
+int hv_reserve_workspace(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width) {
+  if (!h) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized) fail(HV_ERR_STATE, "hv_reserve_workspace before hv_finalize");
+    const size_t need = measure(h, B, F, height, width);
+    if (h->private_ws_bytes < need) {
+      if (h->private_ws) ck(cudaFree(h->private_ws), "cudaFree(workspace)");
+      h->private_ws = nullptr;
+      h->private_ws_bytes = 0;
+      ck(cudaMalloc(&h->private_ws, need), "cudaMalloc(workspace)");
+      h->private_ws_bytes = need;
+    }
+  });
+}
+
+int hv_set_timestep_source(hv_handle h, const int64_t* dev_table, const int32_t* dev_index) {
+  if (!h || ((dev_table == nullptr) != (dev_index == nullptr))) return HV_ERR_INVALID;
+  h->ts_table = reinterpret_cast<const long long*>(dev_table);
+  h->ts_index = dev_index;
+  return HV_OK;
+}
+
+int hv_debug_tap_count(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width) {
+  if (!h || !h->finalized) return HV_ERR_INVALID;
+  try {
+    measure(h, B, F, height, width);
+    return static_cast<int>(h->tap_list.size());
+  } catch (const Err& e) {
+    h->err = e.msg;
+    return e.code;
+  }
+}
+
+int hv_debug_tap_info(hv_handle h, int32_t i, char* name, int32_t name_cap, int64_t* dims4) {
+  if (!h || !name || !dims4 || i < 0 || i >= static_cast<int>(h->tap_list.size()) || name_cap <= 0) return HV_ERR_INVALID;
+  const auto& t = h->tap_list[i];
+  snprintf(name, static_cast<size_t>(name_cap), "%s", t.name.c_str());
+  dims4[0] = t.NF; dims4[1] = t.H; dims4[2] = t.W; dims4[3] = t.C;
+  return HV_OK;
+}
+
+int hv_debug_set_taps(hv_handle h, void* const* dst, int32_t n) {
+  if (!h || n < 0 || (n > 0 && !dst)) return HV_ERR_INVALID;
+  h->tap_dst.assign(dst, dst + n);
+  return HV_OK;
 }
 
 size_t hv_workspace_bytes(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width) {

@@ -1,6 +1,5 @@
 // GroupNorm (+SiLU) and LayerNorm (+cross-attention residual, +temporal positional encoding) on channels-last fp16.
-// Both are HBM-bound passes: fp32 statistics, fp16 rounding exactly where the reference's eager fp16 modules round
-// (after the norm, after SiLU, after the PE add).
+// Both are HBM-bound passes: fp32 statistics and fp32 arithmetic through norm -> SiLU / PE add, one fp16 rounding at the store.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -149,7 +148,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
     unpack8(u, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = r16(fmaf(f[j], sc[j], sh[j]));
+      float y = fmaf(f[j], sc[j], sh[j]);
       if (silu) y = __fdividef(y, 1.0f + __expf(-y));
       f[j] = y;
     }
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
         float a[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(add + vi * 8)), a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j] + a[j]);
+        for (int j = 0; j < 8; ++j) v[k][j] += a[j];
         if (x_out) *reinterpret_cast<uint4*>(x_out + row * C + vi * 8) = pack8(v[k]);
       }
 #pragma unroll
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
         float pv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(pe_row + vi * 8)), pv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[k][j] = r16(v[k][j]) + pv[j];
+        for (int j = 0; j < 8; ++j) v[k][j] += pv[j];
       }
       *reinterpret_cast<uint4*>(out + row * C + vi * 8) = pack8(v[k]);
     }

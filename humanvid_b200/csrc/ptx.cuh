@@ -304,7 +304,16 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- misc
-__device__ __forceinline__ float r16(float v) { return __half2float(__float2half_rn(v)); }  // round through fp16
+// a += lo(h2), b += hi(h2): fp32 accumulators plus the two halves of a packed fp16 pair, one FHADD each (mixed-precision
+// add.f32.f16, sm_100a) -- no separate half -> float conversion.
+__device__ __forceinline__ void add_h2(float& a, float& b, uint32_t h2) {
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.rn.f32.f16 %0, lo, %0;\n\t"
+      "add.rn.f32.f16 %1, hi, %1;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "r"(h2));
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

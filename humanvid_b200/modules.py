@@ -70,7 +70,7 @@ class TemporalBasicTransformerBlock(_Shell):
     """Parameter shell of src/models/attention.py:298-379; ``bank`` is what ReferenceAttentionControl.update fills."""
 
     def __init__(self, dim, cross_attention_dim):
-        super().__init__()
+        nn.Module.__init__(self)   # not super(): an adopted reference class (see _adopt_reference_class) sits later in the MRO
         self.attn1 = _Attention(dim)
         self.norm1 = nn.LayerNorm(dim)
         self.attn2 = _Attention(dim, cross_attention_dim)
@@ -84,12 +84,34 @@ class BasicTransformerBlock(TemporalBasicTransformerBlock):
     """Writer-side block of the 2-D reference UNet (src/models/attention.py BasicTransformerBlock): same parameters."""
 
 
+_ADOPTED = {}
+
+
+def _adopt_reference_class(cls):
+    """Inside the reference tree its own ``ReferenceAttentionControl`` finds the blocks to hook with
+    ``isinstance(module, src.models.attention.TemporalBasicTransformerBlock / BasicTransformerBlock)``
+    (mutual_self_attention.py:284-300, 321-330).  A native UNet built there must not silently present zero blocks (banks
+    would never arrive): when ``src.models.attention`` is loaded, the shells are instantiated from a subclass that also derives
+    from the reference's class of the same name, so the reference's control walks, sorts, hooks and fills ``.bank`` on them
+    exactly as on its own modules.  (The hooked ``forward`` is never called; the native forward reads ``.bank``.)"""
+    import sys
+
+    ref_mod = sys.modules.get("src.models.attention")
+    ref = getattr(ref_mod, cls.__name__, None) if ref_mod is not None else None
+    if not (isinstance(ref, type) and issubclass(ref, nn.Module)) or issubclass(cls, ref):
+        return cls
+    key = (cls, ref)
+    if key not in _ADOPTED:
+        _ADOPTED[key] = type(cls.__name__, (cls, ref), {"__module__": cls.__module__, "__doc__": cls.__doc__})
+    return _ADOPTED[key]
+
+
 class _Transformer3D(_Shell):
     def __init__(self, ch, cross_attention_dim, groups, block_cls=None):
         super().__init__()
         self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
         self.proj_in = _conv(ch, ch, 1)
-        self.transformer_blocks = nn.ModuleList([(block_cls or TemporalBasicTransformerBlock)(ch, cross_attention_dim)])
+        self.transformer_blocks = nn.ModuleList([_adopt_reference_class(block_cls or TemporalBasicTransformerBlock)(ch, cross_attention_dim)])
         self.proj_out = _conv(ch, ch, 1)
 
 
@@ -130,6 +152,8 @@ class _TemporalTransformer3D(_Shell):
         self.proj_in = nn.Linear(ch, ch)
         self.transformer_blocks = nn.ModuleList([_TemporalBlock(ch, 2, max_len)])
         self.proj_out = nn.Linear(ch, ch)
+        nn.init.zeros_(self.proj_out.weight)   # zero_module (motion_module.py:72-75): an unloaded motion module is the identity
+        nn.init.zeros_(self.proj_out.bias)
 
 
 class _MotionModule(_Shell):
@@ -193,6 +217,9 @@ class _NativeNet(nn.Module):
         self._handle = None
         self._pushed_versions = None
         self._epoch = 0
+        self._bank_fp = None
+        self._bank_refs = None
+        self._reserved = set()
 
     def _hv_config(self) -> "HvConfig":  # pragma: no cover - overridden
         raise NotImplementedError
@@ -206,9 +233,15 @@ class _NativeNet(nn.Module):
         return next(self.parameters()).device
 
     def _versions(self):
-        # cheap fingerprint checked on every forward; full re-push is forced by load_state_dict()/.to()/.half()
+        # fingerprint checked on every forward: in-place edits of ANY parameter / buffer (sum of their version counters), a
+        # re-allocation or dtype change of the first one, and load_state_dict()/.to()/.half() (the epoch) all force a re-push
         p = next(self.parameters())
-        return (p.data_ptr(), p._version, p.dtype, self._epoch)
+        ver = 0
+        for t in self.parameters():
+            ver += t._version
+        for t in self.buffers():
+            ver += t._version
+        return (p.data_ptr(), ver, p.dtype, self._epoch)
 
     def _apply(self, fn, *a, **k):
         self._epoch = getattr(self, "_epoch", 0) + 1
@@ -226,6 +259,17 @@ class _NativeNet(nn.Module):
         if self._handle is not None:
             N.lib().hv_destroy(self._handle)
             self._handle = None
+        # a new handle may be created at the same address: nothing cached against the old one may survive it
+        self._bank_fp = None
+        self._bank_refs = None
+        self._reserved = set()
+
+    def _reserve(self, h, B, F, H, W):
+        """The C forwards never allocate: grow the handle's private workspace here, once per new shape."""
+        key = (B, F, H, W)
+        if key not in self._reserved:
+            N.check(N.lib().hv_reserve_workspace(h, N.i32(B), N.i32(F), N.i32(H), N.i32(W)), h)
+            self._reserved.add(key)
 
     def __del__(self):
         try:
@@ -394,6 +438,7 @@ class UNet3DConditionModel(_NativeNet):
         self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=norm_eps)
         self.conv_out = _conv(ch[0], out_channels, 3, padding=1)
         self._ref_cfg = True
+        self._forward_flags = None   # humanvid_b200.distributed sets HV_FLAG_UNCOND_ONLY / HV_FLAG_COND_ONLY for one-half units
 
     # ---- reference banks (ReferenceAttentionControl, read side) -----------------------------------------------
     def reader_blocks(self) -> List[TemporalBasicTransformerBlock]:
@@ -441,6 +486,29 @@ class UNet3DConditionModel(_NativeNet):
         cfg.use_motion_module, cfg.motion_max_len = int(self._mm), self._max_len
         return cfg
 
+    # ---- debug taps (per-layer error ladder; scripts/error_ladder.py) ---------------------------------------------------
+    def debug_tap_plan(self, B, F, h, w):
+        """[(reference module path, (NF, H, W, C))] of the activations the native forward can copy out, in execution order."""
+        hd = self._sync_native()
+        lib = N.lib()
+        n = lib.hv_debug_tap_count(hd, N.i32(B), N.i32(F), N.i32(h), N.i32(w))
+        if n < 0:
+            N.check(n, hd)
+        plan = []
+        for i in range(n):
+            name = C.create_string_buffer(128)
+            dims = (C.c_int64 * 4)()
+            N.check(lib.hv_debug_tap_info(hd, N.i32(i), name, N.i32(128), dims), hd)
+            plan.append((name.value.decode(), tuple(int(d) for d in dims)))
+        return plan
+
+    def debug_set_taps(self, tensors):
+        """tensors[i] (or None) receives tap i as channels-last fp16 (NF, H, W, C) on the next forwards; [] disables."""
+        hd = self._sync_native()
+        self._tap_refs = list(tensors)
+        arr = (C.c_void_p * max(len(tensors), 1))(*[None if t is None else t.data_ptr() for t in tensors])
+        N.check(N.lib().hv_debug_set_taps(hd, arr if tensors else None, N.i32(len(tensors))), hd)
+
     def workspace_bytes(self, B, F, h, w) -> int:
         hd = self._sync_native()
         f = N.lib().hv_workspace_bytes
@@ -467,6 +535,11 @@ class UNet3DConditionModel(_NativeNet):
         B, Cc, F, H, W = sample.shape
         if Cc != self.in_channels:
             raise ValueError(f"sample has {Cc} channels, model expects {self.in_channels}")
+        if F > 1 and not self.config.use_inflated_groupnorm:
+            # resnet.py:158-161: with use_inflated_groupnorm=False the reference applies nn.GroupNorm to the 5-D tensor, pooling the
+            # statistics over frames; the native path normalises per frame (InflatedGroupNorm), identical only when F == 1
+            raise NotImplementedError("use_inflated_groupnorm=False with more than one frame (cross-frame GroupNorm statistics) is not implemented; "
+                                      "the inference_v2 configuration sets use_inflated_groupnorm=True")
         h = self._sync_native()
         self._push_banks(h)
         x = self._as_half(sample, "sample")
@@ -478,7 +551,8 @@ class UNet3DConditionModel(_NativeNet):
             raise ValueError(f"pose_cond_fea must be {(B, self.config.block_out_channels[0], F, H, W)}, got {tuple(pose.shape)}")
         t = int(timestep.reshape(-1)[0].item()) if torch.is_tensor(timestep) else int(timestep)
         out = torch.empty((B, self.config.out_channels, F, H, W), device=x.device, dtype=torch.float16)
-        flags = 1 if self._ref_cfg else 0
+        flags = self._forward_flags if self._forward_flags is not None else (1 if self._ref_cfg else 0)
+        self._reserve(h, B, F, H, W)
         N.check(N.lib().hv_unet3d_forward(h, N.ptr(x), N.i64(t), N.ptr(ehs), N.ptr(pose), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W),
                                           C.c_uint32(flags), None, C.c_size_t(0), N.stream()), h)
         out = out.to(sample.dtype) if sample.dtype != torch.float16 else out
@@ -490,7 +564,10 @@ class UNet3DConditionModel(_NativeNet):
     @classmethod
     def from_pretrained_2d(cls, pretrained_model_path, motion_module_path, subfolder=None, unet_additional_kwargs=None, mm_zero_proj_out=False):
         path = os.path.join(str(pretrained_model_path), subfolder) if subfolder is not None else str(pretrained_model_path)
-        with open(os.path.join(path, "config.json")) as f:
+        config_file = os.path.join(path, "config.json")
+        if not (os.path.exists(config_file) and os.path.isfile(config_file)):
+            raise RuntimeError(f"{config_file} does not exist or is not a file")
+        with open(config_file) as f:
             cfg = json.load(f)
         cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
         cfg["down_block_types"] = ["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"]
@@ -508,15 +585,21 @@ class UNet3DConditionModel(_NativeNet):
 
             state = load_file(st_path, device="cpu")
         else:
-            state = torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu", weights_only=True)
+            bin_path = os.path.join(path, "diffusion_pytorch_model.bin")
+            if not os.path.isfile(bin_path):
+                raise FileNotFoundError(f"no weights file found in {path}")
+            state = torch.load(bin_path, map_location="cpu", weights_only=True)
         mp = str(motion_module_path)
-        if os.path.isfile(mp):
-            if mp.endswith(".safetensors"):
+        if os.path.exists(mp) and os.path.isfile(mp):
+            suffix = os.path.splitext(mp)[1].lower()
+            if suffix in (".pth", ".pt", ".ckpt"):
+                mm_state = torch.load(mp, map_location="cpu", weights_only=True)
+            elif suffix == ".safetensors":
                 from safetensors.torch import load_file
 
                 mm_state = load_file(mp, device="cpu")
             else:
-                mm_state = torch.load(mp, map_location="cpu", weights_only=True)
+                raise RuntimeError(f"unknown file format for motion module weights: {suffix}")
             if mm_zero_proj_out:
                 mm_state = {k: v for k, v in mm_state.items() if "proj_out" not in k}
             state.update({k: v for k, v in mm_state.items() if "motion_modules" in k})
@@ -656,6 +739,7 @@ class UNet2DConditionModel(_NativeNet):
         banks = [torch.empty((B, (H >> lvl) * (W >> lvl), blk.norm1.normalized_shape[0]), device=x.device, dtype=torch.float16) for blk, lvl in blocks]
         hidden = torch.empty((B, self.config.block_out_channels[0], H, W), device=x.device, dtype=torch.float16)
         ptrs = (C.c_void_p * len(banks))(*[b.data_ptr() for b in banks])
+        self._reserve(h, B, 1, H, W)
         N.check(N.lib().hv_unet2d_reference_forward(h, N.ptr(x), N.i64(t), N.ptr(ehs), N.ptr(hidden), ptrs, N.i32(len(banks)), N.i32(B), N.i32(H), N.i32(W),
                                                     None, C.c_size_t(0), N.stream()), h)
         if self._ref_write:
@@ -723,6 +807,7 @@ class PoseGuider(_NativeNet):
         h = self._sync_native()
         x = self._as_half(conditioning, "conditioning")
         out = torch.empty((B, self._cfg[0], F, H // 8, W // 8), device=x.device, dtype=torch.float16)
+        self._reserve(h, B, F, H, W)
         N.check(N.lib().hv_pose_guider_forward(h, N.ptr(x), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W), None, C.c_size_t(0), N.stream()), h)
         return out.to(conditioning.dtype) if conditioning.dtype != torch.float16 else out
 
@@ -786,6 +871,7 @@ class CameraPoseEncoder(_NativeNet):
         h = self._sync_native()
         xin = self._as_half(x, "plucker embedding")
         out = torch.empty((B * F, self._cfg["c"], H // r, W // r), device=xin.device, dtype=torch.float16)
+        self._reserve(h, B, F, H, W)
         N.check(N.lib().hv_camera_encoder_forward(h, N.ptr(xin), N.ptr(out), N.i32(B), N.i32(F), N.i32(H), N.i32(W), None, C.c_size_t(0), N.stream()), h)
         return [out.to(x.dtype) if x.dtype != torch.float16 else out]
 

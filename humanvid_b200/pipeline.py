@@ -38,6 +38,32 @@ def uniform(step: int = 0, num_steps: Optional[int] = None, num_frames: int = 0,
             yield [e % num_frames for e in range(j, j + context_size * context_step, context_step)]
 
 
+# ---- latent interpolation (src/pipelines/utils.py) -----------------------------------------------------------------
+tensor_interpolation = None
+
+
+def get_tensor_interpolation_method():
+    return tensor_interpolation
+
+
+def set_tensor_interpolation_method(is_slerp):
+    global tensor_interpolation
+    tensor_interpolation = slerp if is_slerp else linear
+
+
+def linear(v1, v2, t):
+    return (1.0 - t) * v1 + t * v2
+
+
+def slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, DOT_THRESHOLD: float = 0.9995) -> torch.Tensor:
+    u0, u1 = v0 / v0.norm(), v1 / v1.norm()
+    dot = (u0 * u1).sum()
+    if dot.abs() > DOT_THRESHOLD:
+        return (1.0 - t) * v0 + t * v1
+    omega = dot.acos()
+    return (((1.0 - t) * omega).sin() * v0 + (t * omega).sin() * v1) / omega.sin()
+
+
 def get_context_scheduler(name: str) -> Callable:
     if name == "uniform":
         return uniform
@@ -64,7 +90,9 @@ def _to_tensor_image(img, height, width, lo_hi=(-1.0, 1.0)):
             t = torch.nn.functional.interpolate(t, size=(height, width), mode="bilinear", align_corners=False)
         return t
     if hasattr(img, "resize"):
-        img = img.convert("RGB").resize((width, height))
+        from PIL import Image
+
+        img = img.convert("RGB").resize((width, height), resample=Image.LANCZOS)   # VaeImageProcessor's default resample
         arr = np.asarray(img).astype(np.float32) / 255.0
     else:
         arr = np.asarray(img).astype(np.float32)
@@ -81,11 +109,19 @@ class _PipelineBase:
         self.vae, self.image_encoder, self.reference_unet = vae, image_encoder, reference_unet
         self.denoising_unet, self.pose_guider, self.camera_pose_encoder = denoising_unet, pose_guider, camera_pose_encoder
         self.scheduler = scheduler
+        if clip_image_processor is None:
+            # the reference always builds one (pipeline_pose2vid_long.py:73): CLIP mean/std normalisation + bicubic resize
+            from transformers import CLIPImageProcessor
+
+            clip_image_processor = CLIPImageProcessor()
         self.clip_image_processor = clip_image_processor
         cfg = getattr(vae, "config", None)
         n = len(getattr(cfg, "block_out_channels", (1, 2, 3, 4))) if cfg is not None else 4
         self.vae_scale_factor = 2 ** (n - 1)
         self.cache_condition_features = True
+        self.vae_decode_batch = 8
+        self.device_step_loop = True     # window gather / accumulate / CFG / DDIM on the device, one CUDA graph per step
+        self.use_cuda_graph = True
         self.reference_control_cls = None  # (writer_cls, reader_cls); set by the integrator, see INTEGRATION.md
 
     def to(self, device=None, dtype=None):
@@ -110,19 +146,61 @@ class _PipelineBase:
         return latents * self.scheduler.init_noise_sigma
 
     def _clip_embed(self, ref_image, device):
-        if callable(getattr(self, "clip_image_processor", None)) or hasattr(self.clip_image_processor, "preprocess"):
-            pix = self.clip_image_processor.preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
+        if torch.is_tensor(ref_image):
+            # tensor images (tests, already-decoded inputs) in [-1, 1]: resize, map to [0, 1], CLIP mean / std
+            pix = _to_tensor_image(ref_image, 224, 224).to(device) * 0.5 + 0.5
+            mean = torch.tensor(self.clip_image_processor.image_mean, device=pix.device).view(1, 3, 1, 1)
+            std = torch.tensor(self.clip_image_processor.image_std, device=pix.device).view(1, 3, 1, 1)
+            pix = (pix - mean) / std
         else:
-            pix = _to_tensor_image(ref_image, 224, 224, (0.0, 1.0))
+            pix = self.clip_image_processor.preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
         enc_dtype = next(self.image_encoder.parameters()).dtype if hasattr(self.image_encoder, "parameters") else torch.float16
         return self.image_encoder(pix.to(device, dtype=enc_dtype)).image_embeds
+
+    def _device_loop_ok(self, eta, callback, context_batch_size, context_queue, latents) -> bool:
+        """The on-device loop covers what scripts/pose2vid.py uses: native denoising UNet, this package's DDIM scheduler with
+        eta = 0, no per-step host callback, one window per UNet call, equally long windows."""
+        from .modules import UNet3DConditionModel
+        from .scheduler import DDIMScheduler
+
+        return (self.device_step_loop and isinstance(self.denoising_unet, UNet3DConditionModel) and isinstance(self.scheduler, DDIMScheduler)
+                and eta == 0.0 and callback is None and context_batch_size == 1 and latents.is_cuda
+                and len({len(c) for c in context_queue}) == 1 and len(context_queue) <= 32)
+
+    def _loop_kwargs(self, context_queue, cfg_on):
+        """Extra DeviceDenoiseLoop arguments; humanvid_b200.distributed overrides this to split (window x CFG-half) units over ranks."""
+        return {}
+
+    def interpolate_latents(self, latents: torch.Tensor, interpolation_factor: int, device):
+        """pipeline_pose2vid_long.py:294-336: (factor - 1) interpolated latents between consecutive frames."""
+        if interpolation_factor < 2:
+            return latents
+        if tensor_interpolation is None:
+            raise RuntimeError("interpolation_factor >= 2 needs set_tensor_interpolation_method(is_slerp) first (src/pipelines/utils.py)")
+        new_latents = torch.zeros((latents.shape[0], latents.shape[1], ((latents.shape[2] - 1) * interpolation_factor) + 1, latents.shape[3],
+                                   latents.shape[4]), device=latents.device, dtype=latents.dtype)
+        rate = [i / interpolation_factor for i in range(interpolation_factor)][1:]
+        new_index = 0
+        v1 = None
+        for i0, i1 in zip(range(latents.shape[2]), range(latents.shape[2])[1:]):
+            v0, v1 = latents[:, :, i0], latents[:, :, i1]
+            new_latents[:, :, new_index] = v0
+            new_index += 1
+            for f in rate:
+                new_latents[:, :, new_index] = tensor_interpolation(v0.to(device=device), v1.to(device=device), f).to(latents.device)
+                new_index += 1
+        new_latents[:, :, new_index] = v1
+        return new_latents
 
     def decode_latents(self, latents):
         video_length = latents.shape[2]
         latents = 1 / 0.18215 * latents
         b = latents.shape[0]
         latents = latents.permute(0, 2, 1, 3, 4).reshape(b * video_length, *latents.shape[1:2], *latents.shape[3:])
-        video = [self.vae.decode(latents[i : i + 1]).sample for i in range(latents.shape[0])]
+        # the reference decodes one frame per call (:119-121); frames are independent in the VAE, so they go `vae_decode_batch` at a
+        # time (SURVEY 8f-4).  vae_decode_batch = 1 reproduces the reference's call pattern exactly.
+        n = max(1, int(self.vae_decode_batch))
+        video = [self.vae.decode(latents[i : i + n]).sample for i in range(0, latents.shape[0], n)]
         video = torch.cat(video)
         video = video.reshape(b, video_length, *video.shape[1:]).permute(0, 2, 1, 3, 4)
         video = (video / 2 + 0.5).clamp(0, 1)
@@ -170,32 +248,54 @@ class Pose2VideoPipeline(_PipelineBase):
         context_scheduler = get_context_scheduler(context_schedule)
         feature_cache = {}
 
-        for i, t in enumerate(timesteps):
-            noise_pred = torch.zeros((latents.shape[0] * (2 if cfg_on else 1), *latents.shape[1:]), device=latents.device, dtype=latents.dtype)
-            counter = torch.zeros((1, 1, latents.shape[2], 1, 1), device=latents.device, dtype=latents.dtype)
-            if i == 0 and writer is not None:
+        def window_features(context):
+            key = tuple(tuple(c) for c in context)
+            if self.cache_condition_features and key in feature_cache:
+                return feature_cache[key]
+            pose_fea = self.pose_guider(torch.cat([pose_cond_tensor[:, :, c] for c in context]))
+            cur_cam = torch.cat([camera_embedding[:, :, c] for c in context])
+            cam_b = cur_cam.shape[0]
+            cam = self.camera_pose_encoder(cur_cam)[0]
+            cam = cam.reshape(cam_b, -1, *cam.shape[1:]).permute(0, 2, 1, 3, 4)
+            cond = (pose_fea + cam).repeat(2 if cfg_on else 1, 1, 1, 1, 1)
+            if self.cache_condition_features:
+                feature_cache[key] = cond
+            return cond
+
+        def write_banks():
+            if writer is not None:
                 self.reference_unet(ref_image_latents.repeat((2 if cfg_on else 1), 1, 1, 1), torch.zeros((), dtype=torch.long, device=device),
                                     encoder_hidden_states=encoder_hidden_states, return_dict=False)
                 reader.update(writer)
-            context_queue = list(context_scheduler(0, num_inference_steps, latents.shape[2], context_frames, context_stride, context_overlap))
+
+        # the scheduler is always asked with step = 0 (:495-502): the windows are the same at every timestep
+        context_queue = list(context_scheduler(0, num_inference_steps, latents.shape[2], context_frames, context_stride, context_overlap))
+        if self._device_loop_ok(eta, callback, context_batch_size, context_queue, latents):
+            # ---- every per-timestep operation on the device, one CUDA graph per step -------------------------
+            from .device_loop import DeviceDenoiseLoop
+
+            write_banks()
+            conds = [window_features([c]) for c in context_queue]
+            loop = DeviceDenoiseLoop(self.denoising_unet, self.scheduler, latents, context_queue, encoder_hidden_states, conds, guidance_scale, cfg_on,
+                                     **self._loop_kwargs(context_queue, cfg_on))
+            try:
+                latents = loop.run(len(timesteps), use_graph=self.use_cuda_graph).to(latents.dtype).clone()
+            finally:
+                loop.close()
+            timesteps = []
+
+        for i, t in enumerate(timesteps):
+            noise_pred = torch.zeros((latents.shape[0] * (2 if cfg_on else 1), *latents.shape[1:]), device=latents.device, dtype=latents.dtype)
+            counter = torch.zeros((1, 1, latents.shape[2], 1, 1), device=latents.device, dtype=latents.dtype)
+            if i == 0:
+                write_banks()
             nb = math.ceil(len(context_queue) / context_batch_size)
             global_context = [context_queue[k * context_batch_size : (k + 1) * context_batch_size] for k in range(nb)]
             for context in global_context:
                 latent_model_input = torch.cat([latents[:, :, c] for c in context]).to(device).repeat(2 if cfg_on else 1, 1, 1, 1, 1)
                 latent_model_input = self.scheduler.scale_model_input(latent_model_input, t)
                 b = latent_model_input.shape[0]
-                key = tuple(tuple(c) for c in context)
-                if self.cache_condition_features and key in feature_cache:
-                    cond = feature_cache[key]
-                else:
-                    pose_fea = self.pose_guider(torch.cat([pose_cond_tensor[:, :, c] for c in context]))
-                    cur_cam = torch.cat([camera_embedding[:, :, c] for c in context])
-                    cam_b = cur_cam.shape[0]
-                    cam = self.camera_pose_encoder(cur_cam)[0]
-                    cam = cam.reshape(cam_b, -1, *cam.shape[1:]).permute(0, 2, 1, 3, 4)
-                    cond = (pose_fea + cam).repeat(2 if cfg_on else 1, 1, 1, 1, 1)
-                    if self.cache_condition_features:
-                        feature_cache[key] = cond
+                cond = window_features(context)
                 pred = self.denoising_unet(latent_model_input, t, encoder_hidden_states=encoder_hidden_states[:b], pose_cond_fea=cond,
                                            return_dict=False)[0]
                 for c in context:
@@ -210,6 +310,8 @@ class Pose2VideoPipeline(_PipelineBase):
         reader.clear()
         if writer is not None:
             writer.clear()
+        if interpolation_factor > 0:
+            latents = self.interpolate_latents(latents, interpolation_factor, device)
         if output_type == "latent":
             return latents if not return_dict else Pose2VideoPipelineOutput(videos=latents)
         images = self.decode_latents(latents)
@@ -248,9 +350,17 @@ class Pose2ImagePipeline(_PipelineBase):
         ref_latents = self.vae.encode(_to_tensor_image(ref_image, height, width).to(dtype=vae_dtype, device=device)).latent_dist.mean * 0.18215
         pose = _to_tensor_image(pose_image, height, width, (0.0, 1.0)).unsqueeze(2).to(device=device, dtype=self.pose_guider.dtype)
         pose_fea = self.pose_guider(pose)
-        cam = self.camera_pose_encoder(camera_embedding.to(device=device, dtype=self.camera_pose_encoder.dtype))[0]
-        cam = cam.reshape(1, -1, *cam.shape[1:]).permute(0, 2, 1, 3, 4)
-        cond = (pose_fea + cam).repeat(2 if cfg_on else 1, 1, 1, 1, 1)
+        camera_embedding = camera_embedding.to(device=device, dtype=self.camera_pose_encoder.dtype)
+        if camera_embedding.ndim == 4:                    # (b, 6, h, w): the reference unsqueezes the frame axis itself (pipeline_pose2img.py:298)
+            camera_embedding = camera_embedding.unsqueeze(2)
+        assert camera_embedding.ndim == 5
+        cb = camera_embedding.shape[0]
+        cam = self.camera_pose_encoder(camera_embedding)[0]
+        cam = cam.reshape(cb, -1, *cam.shape[1:]).permute(0, 2, 1, 3, 4)
+        cond = pose_fea + cam
+        if cond.shape[0] != latents.shape[0]:             # num_images_per_prompt > 1: one condition for every image of the prompt
+            cond = cond.repeat(latents.shape[0] // cond.shape[0], 1, 1, 1, 1)
+        cond = cond.repeat(2 if cfg_on else 1, 1, 1, 1, 1)
         for i, t in enumerate(timesteps):
             if i == 0 and writer is not None:
                 self.reference_unet(ref_latents.repeat((2 if cfg_on else 1), 1, 1, 1), torch.zeros((), dtype=torch.long, device=device),

@@ -49,6 +49,17 @@ class DDIMScheduler:
         self.timesteps = torch.from_numpy(ts.astype(np.int64)).to(device)
         self._host_timesteps = [int(v) for v in ts]
 
+    def coef_table(self):
+        """[num_inference_steps][4] fp32: sqrt(a_t), sqrt(1 - a_t), sqrt(a_prev), sqrt(1 - a_prev) per step -- what ``step`` uses,
+        laid out for the device-side loop (hv_op_cfg_ddim_step reads row ``*step_index``)."""
+        rows = []
+        for t in self._host_timesteps:
+            prev = t - self.config.num_train_timesteps // self.num_inference_steps
+            a_t = float(self.alphas_cumprod[t])
+            a_p = float(self.alphas_cumprod[prev]) if prev >= 0 else 1.0
+            rows.append([a_t**0.5, (1 - a_t) ** 0.5, a_p**0.5, (1 - a_p) ** 0.5])
+        return torch.tensor(rows, dtype=torch.float32)
+
     def scale_model_input(self, sample, timestep=None):
         return sample
 

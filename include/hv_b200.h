@@ -33,8 +33,12 @@ typedef struct hv_model* hv_handle;
 enum hv_kind { HV_KIND_UNET3D = 0, HV_KIND_POSE_GUIDER = 1, HV_KIND_CAMERA_ENCODER = 2, HV_KIND_UNET2D_REF = 3 };
 enum hv_dtype { HV_F16 = 0, HV_F32 = 1 };
 enum hv_forward_flags {
-  HV_FLAG_CFG = 1 /* batch = [uncond half ; cond half]: the first half ignores the reference banks
-                     (mutual_self_attention.py:166-186) */
+  HV_FLAG_CFG = 1,         /* batch = [uncond half ; cond half]: the first half ignores the reference banks
+                              (mutual_self_attention.py:166-186) */
+  HV_FLAG_UNCOND_ONLY = 2, /* the batch is an unconditional CFG half only (one unit of a (window x CFG-half) split over
+                              GPUs): no item reads the banks */
+  HV_FLAG_COND_ONLY = 4    /* the batch is a conditional CFG half only: its B items read the LAST B items of the banks
+                              (banks are written for [uncond ; cond], pipeline_pose2vid_long.py:470-480) */
 };
 
 typedef struct hv_config {
@@ -81,9 +85,16 @@ int hv_clear_ref_banks(hv_handle h);
 
 /* Bytes of scratch one forward needs at this shape (h, w = spatial size of the tensor entering the network). */
 size_t hv_workspace_bytes(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width);
+/* Grows the handle's private workspace to what this shape needs (cudaMalloc here, never inside a forward).  A forward
+ * called with workspace == NULL uses it and fails with HV_ERR_STATE if it is too small. */
+int hv_reserve_workspace(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width);
+/* Device-resident timestep for CUDA-graph replay of a denoising loop (pipeline_pose2vid_long.py:454-563): when set, every
+ * UNet forward of this handle embeds dev_table[*dev_index] (read on the device when the kernel runs) and ignores its
+ * `timestep` argument.  Both NULL restores the host argument. */
+int hv_set_timestep_source(hv_handle h, const int64_t* dev_table, const int32_t* dev_index);
 
 /* sample (B,4,F,h,w), encoder_hidden_states (B,1,cross_attention_dim), pose_cond_fea (B,320,F,h,w) or NULL,
- * out (B,4,F,h,w); all fp16.  workspace may be NULL (the handle then keeps a private one). */
+ * out (B,4,F,h,w); all fp16.  workspace may be NULL: the handle's reserved workspace (hv_reserve_workspace) is used. */
 int hv_unet3d_forward(hv_handle h, const void* sample, int64_t timestep, const void* encoder_hidden_states, const void* pose_cond_fea,
                       void* out, int32_t B, int32_t F, int32_t height, int32_t width, uint32_t flags, void* workspace,
                       size_t ws_bytes, hv_stream_t stream);
@@ -101,6 +112,14 @@ int hv_pose_guider_forward(hv_handle h, const void* conditioning, void* out, int
 /* plucker (B,6,F,H,W) -> out (B*F,320,H/8,W/8) (the single feature map of the one-level encoder) */
 int hv_camera_encoder_forward(hv_handle h, const void* plucker, void* out, int32_t B, int32_t F, int32_t H, int32_t W,
                               void* workspace, size_t ws_bytes, hv_stream_t stream);
+
+/* Debug taps (per-layer error ladder, profiles/): the activation leaving the i-th block of the UNet forward (conv_in, every
+ * resnet / transformer / motion module / down- / up-sampler, in execution order) is copied to dst[i] as channels-last fp16
+ * (NF, H, W, C).  hv_debug_tap_count plans the forward at this shape and returns the number of taps; hv_debug_tap_info
+ * names tap i (the reference's module path) and gives dims4 = {NF, H, W, C}; hv_debug_set_taps(h, NULL, 0) disables. */
+int hv_debug_tap_count(hv_handle h, int32_t B, int32_t F, int32_t height, int32_t width);
+int hv_debug_tap_info(hv_handle h, int32_t i, char* name, int32_t name_cap, int64_t* dims4);
+int hv_debug_set_taps(hv_handle h, void* const* dst, int32_t n);
 
 /* Kernel launches issued by the last forward on this handle (bench.py's gpu_launches). */
 int64_t hv_last_launch_count(hv_handle h);

@@ -39,9 +39,9 @@ enum hv_status {
 
 enum hv_act { HV_ACT_NONE = 0, HV_ACT_RELU = 1, HV_ACT_SILU = 2 };
 
-/* Fused epilogue of hv_op_gemm / hv_op_conv3x3, applied in this order with fp16 rounding after each step exactly
- * where the reference's eager fp16 modules round:  v = acc + bias; v += rowvec[row / rows_per_group]; v = act(v);
- * v += residual[row].  With geglu != 0 the packed weight holds [128 hidden | 128 gate] rows per 256-row block and the
+/* Fused epilogue of hv_op_gemm / hv_op_conv3x3, applied in this order in fp32 with ONE fp16 rounding at the store (the
+ * reference's eager fp16 modules round after every step; the fp32 oracle is the parity anchor):  v = acc + bias;
+ * v += rowvec[row / rows_per_group]; v = act(v); v += residual[row].  With geglu != 0 the packed weight holds [128 hidden | 128 gate] rows per 256-row block and the
  * output is hidden * gelu_erf(gate) with N/2 columns. */
 typedef struct hv_epilogue {
   const void* bias;      /* fp16 [N] or NULL */
@@ -123,6 +123,27 @@ int hv_op_small_linear(const void* X, const void* W, const void* bias, void* out
                        int32_t act_in, hv_stream_t stream);
 /* Timesteps(320, flip_sin_to_cos=True, shift=0): out[b] = [cos(t w_i) | sin(t w_i)] rounded to fp16. */
 int hv_op_timestep_embedding(int64_t timestep, void* out, int64_t B, int64_t dim, hv_stream_t stream);
+
+/* ---- per-timestep glue of Pose2VideoPipeline.__call__ on the device (src/pipelines/pipeline_pose2vid_long.py:516-563) ----
+ * hv_op_window_gather: out[(r*Bl + b), c, i] = latents[b, c, frame_idx[i]] for r < repeat -- `latents[:, :, c].repeat(2, ...)` (:516-523).
+ *   latents (Bl, C, Ftot, HW) fp16; frame_idx: DEVICE int32[Fw]; out (repeat*Bl, C, Fw, HW) fp16.
+ * hv_op_cfg_ddim_step: for every latent element, mean over the windows that contain its frame of the window predictions
+ *   (`noise_pred[:, :, c] += pred; counter[:, :, c] += 1; noise_pred / counter`, :550-556), classifier-free guidance
+ *   `uncond + s (text - uncond)` (:557-559; skipped when pred_cond == NULL) and the DDIM update with eta = 0 (:561-563;
+ *   diffusers DDIMScheduler.step): x0, eps from the model output (prediction_type 0 = v_prediction, 1 = epsilon),
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps, all in fp32, latents updated in place (one fp16 rounding).
+ *   pred_uncond / pred_cond: HOST arrays of n_windows device pointers, each (Bl, C, Fw, HW) fp16 (the two halves of a
+ *   CFG-doubled UNet output are pred and pred + Bl*C*Fw*HW); inv: DEVICE int32 [Ftot][K], entry = window*Fw + position of
+ *   a window slot holding that frame, or -1; coef: DEVICE float [steps][4] = sqrt(a_t), sqrt(1-a_t), sqrt(a_prev),
+ *   sqrt(1-a_prev); step_index: DEVICE int32 (row of coef used; NULL = row 0), read when the kernel runs so that a captured
+ *   CUDA graph of one step replays for every timestep.
+ * hv_op_advance_index: *index += 1 on the device (end of a graph-captured step). */
+int hv_op_window_gather(const void* latents, const int32_t* frame_idx, void* out, int64_t Bl, int64_t C, int64_t Ftot, int64_t Fw, int64_t HW,
+                        int32_t repeat, hv_stream_t stream);
+int hv_op_cfg_ddim_step(const void* const* pred_uncond, const void* const* pred_cond, int32_t n_windows, const int32_t* inv, int32_t K,
+                        const float* coef, const int32_t* step_index, void* latents, int64_t Bl, int64_t C, int64_t Ftot, int64_t Fw, int64_t HW,
+                        float guidance_scale, int32_t prediction_type, hv_stream_t stream);
+int hv_op_advance_index(int32_t* index, hv_stream_t stream);
 
 /* Weight packing (device to device).  conv: fp16 (Cout, Cin, 3, 3) -> [Cout_pad][9*Cin_pad] (zero padded); geglu: rows of a [8C][K] matrix
  * (and its bias) interleaved in 128-row hidden/gate blocks; heads: [heads*d][K] -> [heads*dpad][K] with zero rows. */

@@ -1,0 +1,108 @@
+"""Shapes BASELINE names that config 2 does not exercise:
+
+* config 5's context window: (2, 4, 24, 72, 128) latents (576x1024 clip, 9216 tokens at level 0, different conv boxes / Lp /
+  attention grid than 96x72) with the 16 reference banks, against the oracle in fp32 and in fp16 eager;
+* PoseGuider and CameraPoseEncoder at the full (1, ., 24, 768, 576) input of configs 2-4 (pose_guider.py:51-61,
+  pose_adaptor.py:232-248).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import humanvid_b200 as hv
+    from oracle import hv_oracle as O
+
+from conftest import report
+
+MM_KW = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+             temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+CH, XDIM = (320, 640, 1280, 1280), 768
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def test_config5_window_shape_with_banks():
+    F, H, W = 24, 72, 128
+    ora = O.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).eval()
+    O.synthetic_init(ora, seed=7)
+    ora = ora.half().cuda()
+    nat = hv.UNet3DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM, use_motion_module=True, use_inflated_groupnorm=True,
+                                  motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True, motion_module_type="Vanilla",
+                                  motion_module_kwargs=MM_KW, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    nat.load_state_dict(ora.state_dict())
+    nat = nat.to("cuda", torch.float16)
+    g = torch.Generator(device="cuda").manual_seed(52)
+    x = torch.randn(2, 4, F, H, W, generator=g, device="cuda").half()
+    ehs = torch.randn(2, 1, XDIM, generator=g, device="cuda").half()
+    ehs[:1] = 0
+    pose = (torch.randn(2, CH[0], F, H, W, generator=g, device="cuda") * 0.5).half()
+    banks = [torch.randn(2, l, c, generator=g, device="cuda").half() for (l, c) in O.bank_shapes(ora, H, W)]
+    assert [tuple(b.shape[1:]) for b in banks][-1] == (9216, 320)
+    t = 759
+    with torch.no_grad():
+        plain = nat(x, t, ehs, pose_cond_fea=pose, return_dict=False)[0].clone()
+        ctl = hv.ReferenceAttentionControl(nat, do_classifier_free_guidance=True, mode="read", fusion_blocks="full")
+        for blk, bk in zip(nat.reader_blocks(), banks):
+            blk.bank = [bk]
+        yn = nat(x, t, ehs, pose_cond_fea=pose, return_dict=False)[0].clone()
+        O.set_reference_banks(ora, banks, cfg=True)
+        y16 = ora(x, torch.tensor(t, device="cuda"), ehs, pose_cond_fea=pose)[0]
+        ora.float()
+        O.set_reference_banks(ora, [b.float() for b in banks], cfg=True)
+        y32 = ora(x.float(), torch.tensor(t, device="cuda"), ehs.float(), pose_cond_fea=pose.float())[0]
+        # the two one-half units of the multi-GPU split (HV_FLAG_UNCOND_ONLY / HV_FLAG_COND_ONLY) reproduce the halves of the CFG batch
+        nat._forward_flags = 2
+        y_un = nat(x[:1], t, ehs[:1], pose_cond_fea=pose[:1], return_dict=False)[0].clone()
+        nat._forward_flags = 4
+        y_co = nat(x[1:], t, ehs[1:], pose_cond_fea=pose[1:], return_dict=False)[0].clone()
+        nat._forward_flags = None
+        ctl.clear()
+    torch.cuda.synchronize()
+    e_ref, e_nat, e_pair = rel(y16, y32), rel(yn, y32), rel(yn, y16)
+    report(f"config5 window (2,4,24,72,128) + banks: fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}; "
+           f"unit split vs CFG batch: uncond {rel(y_un, yn[:1]):.1e}, cond {rel(y_co, yn[1:]):.1e}")
+    assert torch.isfinite(yn).all()
+    assert e_nat <= 1.25 * e_ref
+    assert e_nat <= 2e-3
+    assert torch.equal(yn[:1], plain[:1]) and rel(yn[1:], plain[1:]) > 1e-2
+    assert rel(y_un, yn[:1]) <= 5e-4 and rel(y_co, yn[1:]) <= 5e-4
+
+
+def test_pose_guider_and_camera_encoder_full_resolution():
+    F, H, W = 24, 768, 576
+    g = torch.Generator(device="cuda").manual_seed(9)
+    o = O.synthetic_init(O.PoseGuider().eval(), seed=3).half().cuda()
+    pg = hv.PoseGuider(320, block_out_channels=(16, 32, 96, 256))
+    pg.load_state_dict(o.state_dict())
+    pg = pg.to("cuda", torch.float16)
+    x = torch.rand(1, 3, F, H, W, generator=g, device="cuda").half()
+    with torch.no_grad():
+        y = pg(x)
+        y16 = o(x)
+        y32 = o.float()(x.float())
+    torch.cuda.synchronize()
+    assert y.shape == (1, 320, F, H // 8, W // 8)
+    e_pg, e_pg16 = rel(y, y32), rel(y16, y32)
+    del o, y16, y32
+    oc = O.synthetic_init(O.CameraPoseEncoder().eval(), seed=13).half().cuda()
+    cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                               temporal_position_encoding_max_len=24)
+    cam.load_state_dict(oc.state_dict())
+    cam = cam.to("cuda", torch.float16)
+    pl = torch.randn(1, 6, F, H, W, generator=g, device="cuda").half()
+    with torch.no_grad():
+        c = cam(pl)[0]
+        c16 = oc(pl)[0]
+        c32 = oc.float()(pl.float())[0]
+    torch.cuda.synchronize()
+    assert c.shape == (F, 320, H // 8, W // 8)
+    e_cam, e_cam16 = rel(c, c32), rel(c16, c32)
+    report(f"full-resolution (1,.,24,768,576): PoseGuider native vs fp32 {e_pg:.2e} (fp16-eager {e_pg16:.2e}); "
+           f"CameraPoseEncoder native vs fp32 {e_cam:.2e} (fp16-eager {e_cam16:.2e})")
+    assert e_pg <= 1e-3 and e_cam <= 1e-3
