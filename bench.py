@@ -259,6 +259,124 @@ def time_oracle_eager(dev, x, ehs, pose, banks, native_ms, n=5):
                    f"median of {n} after 2 warm-ups"}
 
 
+def time_cond_branches(dev, hbm_gbs, n=5):
+    """PoseGuider (pose_guider.py:51-61) and CameraPoseEncoder (pose_adaptor.py:232-248) at the (1, ., 24, 768, 576) input of configs 2-4: the
+    step-invariant conditioning branches the pipeline runs once per context window.  PoseGuider is HBM-bound small-channel convolution work:
+    achieved GB/s on its ALGORITHMIC bytes (every conv reads its input and writes its output once at the true channel counts)."""
+    import torch
+
+    import humanvid_b200 as hv
+
+    F_, H_, W_ = 24, 768, 576
+    pg = hv.PoseGuider(320, block_out_channels=(16, 32, 96, 256)).to(dev, torch.float16)
+    synthetic_init_(pg, 11, dev)
+    pg.refresh_native()
+    cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                               temporal_position_encoding_max_len=24).to(dev, torch.float16)
+    synthetic_init_(cam, 13, dev)
+    cam.refresh_native()
+    g = torch.Generator(device=dev).manual_seed(5)
+    img = torch.rand(1, 3, F_, H_, W_, generator=g, device=dev).half()
+    pl = torch.randn(1, 6, F_, H_, W_, generator=g, device=dev).half()
+    K = torch.tensor([[[1.788079 * W_ * H_ / W_, 1.788079 * H_, 0.5 * W_, 0.5 * H_]]], device=dev).repeat(1, F_, 1)
+    c2w = torch.eye(4, device=dev).repeat(1, F_, 1, 1)
+
+    def timed(fn):
+        ts = []
+        for i in range(2 + n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    px = F_ * H_ * W_
+    chans = [(3, 16, 1), (16, 16, 1), (16, 32, 2), (32, 32, 1), (32, 96, 2), (96, 96, 1), (96, 256, 2), (256, 320, 1)]
+    nbytes, p = 0, px
+    for cin, cout, st in chans:
+        nbytes += p * cin * 2
+        p //= st * st
+        nbytes += p * cout * 2
+    t_pg, t_cam, t_rays = timed(lambda: pg(img)), timed(lambda: cam(pl)), timed(lambda: cam.forward_cameras(K, c2w, H_, W_))
+    return {"shape": "(1, ., 24, 768, 576)",
+            "pose_guider": {"ms": t_pg, "algorithmic_gb": nbytes / 1e9, "gbs": nbytes / 1e6 / t_pg, "frac_of_hbm_peak": nbytes / 1e6 / t_pg / hbm_gbs,
+                            "launches": pg.last_launch_count,
+                            "note": "16/32/96-channel activations are padded to 64/64/128 channels for the tcgen05 implicit-GEMM kernel: executed traffic is ~2x the algorithmic bytes"},
+            "camera_encoder": {"ms": t_cam, "tflop": 2.18, "tflops": 2.18e3 / t_cam, "launches": cam.last_launch_count},
+            "camera_encoder_from_cameras": {"ms": t_rays, "note": "Plucker embedding generated on the device inside the PixelUnshuffle producer (SURVEY 8f-3); "
+                                            "the 127 MB (1,6,24,768,576) embedding is never built or copied"}}
+
+
+def time_pipeline_clip(dev, unet, steps=25):
+    """The real 25-step Pose2VideoPipeline call (on-device step glue, one CUDA graph per step) with stand-in VAE / CLIP modules (the reference's
+    stay PyTorch and are out of scope) and a native writer UNet: clip latency for one 24-frame 768x576 clip."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+    from types import SimpleNamespace
+
+    import humanvid_b200 as hv
+    from humanvid_b200.pipeline import Pose2VideoPipeline
+
+    class StubVAE(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(3, 4, 8, stride=8)
+            self.config = SimpleNamespace(block_out_channels=(1, 2, 3, 4))
+
+        def encode(self, x):
+            return SimpleNamespace(latent_dist=SimpleNamespace(mean=self.conv(x)))
+
+        def decode(self, z):
+            return SimpleNamespace(sample=Fn.interpolate(z[:, :3], scale_factor=8.0))
+
+    class StubCLIP(nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.lin = nn.Linear(3, dim)
+
+        def forward(self, pix):
+            return SimpleNamespace(image_embeds=self.lin(pix.float().mean((2, 3)).to(self.lin.weight.dtype)))
+
+    H_, W_, F_ = 768, 576, 24
+    ref_unet = hv.UNet2DConditionModel(block_out_channels=CH, cross_attention_dim=XDIM).to(dev, torch.float16)
+    synthetic_init_(ref_unet, 17, dev)
+    ref_unet.refresh_native()
+    pg = hv.PoseGuider(320, block_out_channels=(16, 32, 96, 256)).to(dev, torch.float16)
+    synthetic_init_(pg, 11, dev)
+    pg.refresh_native()
+    cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                               temporal_position_encoding_max_len=24).to(dev, torch.float16)
+    synthetic_init_(cam, 13, dev)
+    cam.refresh_native()
+    pipe = Pose2VideoPipeline(vae=StubVAE().half().to(dev), image_encoder=StubCLIP(XDIM).half().to(dev), reference_unet=ref_unet, denoising_unet=unet,
+                              pose_guider=pg, camera_pose_encoder=cam, scheduler=hv.DDIMScheduler()).to(dev, torch.float16)
+    g = torch.Generator(device=dev).manual_seed(3)
+    ref = torch.rand(3, H_, W_, generator=g, device=dev) * 2 - 1
+    poses = [torch.rand(1, 3, H_, W_, generator=g, device=dev) for _ in range(F_)]
+    camera = torch.randn(1, 6, F_, H_, W_, generator=g, device=dev).half()
+    out = {}
+    for label, n_steps in (("warmup", 2), ("timed", steps)):
+        gen = torch.Generator(device=dev).manual_seed(42)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lat = pipe(ref, poses, camera, W_, H_, F_, n_steps, 3.5, generator=gen, output_type="latent", return_dict=False)
+        torch.cuda.synchronize()
+        out[label] = time.perf_counter() - t0
+    ok = bool(torch.isfinite(lat).all())
+    del pipe, ref_unet, pg, cam
+    torch.cuda.empty_cache()
+    return {"steps": steps, "latency_s": out["timed"], "frames_per_s_per_clip": F_ / out["timed"], "denoise_frames_per_s": F_ * steps / out["timed"], "finite": ok,
+            "what": "humanvid_b200.pipeline.Pose2VideoPipeline.__call__ -> latents: CLIP/VAE stand-ins, native writer UNet2D once, PoseGuider + CameraPoseEncoder once, "
+                    f"{steps} DDIM steps as {steps} replays of one captured CUDA graph (window gather + UNet forward with reference banks + accumulate/CFG/DDIM kernel); "
+                    "wall clock including graph capture"}
+
+
 def run_native(args, rank, world, local_rank, cfg):
     import ctypes as C
 
@@ -419,6 +537,11 @@ def run_native(args, rank, world, local_rank, cfg):
         torch.cuda.synchronize()
         if not (is5 and world > 1):   # (the unit split has no single-GPU forward to compare with)
             eager = time_oracle_eager(dev, sample, ehs, poses[0], banks, ms / len(windows) if is5 else ms)
+    extras = {}
+    if not args.no_extras and world == 1 and not is5:
+        torch.cuda.synchronize()
+        extras["cond_branches"] = time_cond_branches(dev, hbm)
+        extras["pipeline_clip"] = time_pipeline_clip(dev, unet)
     cpu = cpu_reference_sample(cfg, samples=2 if args.quick_cpu else 3) if not args.no_cpu_baseline else None
 
     frames_total = F if is5 else world * F
@@ -453,6 +576,7 @@ def run_native(args, rank, world, local_rank, cfg):
         "op_profile": prof,
         "clocks": clocks,
     }
+    line.update(extras)
     if eager is not None:
         eager["value"] = frames_total / (eager["ms_per_forward"] * (len(windows) if is5 else 1) / 1000.0)
         eager["unit"] = "frames/s"
@@ -477,6 +601,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the fp16-eager oracle timing on the GPU")
     ap.add_argument("--quick-cpu", action="store_true", help="2 instead of 3 timed CPU samples")
+    ap.add_argument("--no-extras", action="store_true", help="skip the conditioning-branch timings and the 25-step pipeline clip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -664,9 +664,14 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         if ((c + 1) * 32 <= kv_valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a0 = fmaf(__uint_as_float(raw[2 * i]), sc, -m_used), a1 = fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used);
+            float a0, a1;   // s * scale - m for two keys in one FFMA2 (bit-identical to two scalar FMAs)
+            upk2(fma2(pk2u(raw[2 * i], raw[2 * i + 1]), pk2(sc, sc), pk2(-m_used, -m_used)), a0, a1);
             if (kDbgNoExp) pk[i] = pack_h2(a0, a1);
-            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
+            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) {   // this pair's exponentials on the FMA pipe (packed fp32x2)
+              float e0, e1;
+              exp2_poly3_x2(a0, a1, e0, e1);
+              pk[i] = pack_h2(e0, e1);
+            }
             else pk[i] = pack_h2(fast_exp2(a0), fast_exp2(a1));
           }
         } else {
@@ -1045,8 +1050,11 @@ struct PPCfg {
   static constexpr bool kFits = 192 + kDv <= 256 && kStages >= 2;
 };
 
-template <int D, int PE, bool TOKEN>
-__global__ void __launch_bounds__(ATTPP_THREADS, 1)   // 18 warps -> 5 on two of the four schedulers -> 16K / (5 * 32) = 102 -> 96 registers
+// MW = 2: one MMA-issuing warp PER GROUP (warp 1 -> group A, warp 18 -> group B).  With a single issuer the loop is in order
+// (S_A, P V_A, S_B, P V_B): group B's next S = Q K^T cannot be issued before group A's probabilities arrive, which locks the two groups
+// into the same phase (both in the MUFU phase, then both waiting -- ncu: XU pipe 69 % busy, B waits ~1.7x longer for S than A).
+template <int D, int PE, bool TOKEN, int MW = 1>
+__global__ void __launch_bounds__(ATTPP_THREADS + 32 * (MW - 1), 1)   // 18 (19) warps -> 5 on a scheduler -> 16K / (5 * 32) = 102 -> 96 registers
 attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
                const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
@@ -1088,9 +1096,9 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&bar_k_full[s], 1);
-      mbar_init(&bar_k_empty[s], 1);
+      mbar_init(&bar_k_empty[s], MW);   // every MMA issuer releases the K / V slot once ITS MMAs on it have completed
       mbar_init(&bar_v_full[s], 1);
-      mbar_init(&bar_v_empty[s], 1);
+      mbar_init(&bar_v_empty[s], MW);
     }
     fence_mbar_init();
     tma_prefetch_desc(&map_q);
@@ -1133,7 +1141,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 18) {
     {   // all 32 lanes run the issue loop with warp-uniform operands; one elected lane issues (see umma_*_w)
       constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
@@ -1162,6 +1170,31 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_wait(bar_q, 0);
       mbar_wait(&bar_k_full[0], 0);
       tc_fence_after();
+      if (MW == 2) {
+        // ---- one issuer per group: S(j+1) goes out as soon as the group has read S(j); P V(j) as soon as its P(j) is in TMEM
+        const int g = warp == 1 ? 0 : 1;
+        issue_s(g, 0);
+        umma_commit_w(&bar_k_empty[0]);
+        for (int j = 0; j < T; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == NS) { nstage = 0; nphase ^= 1; }
+          if (j + 1 < T) {
+            mbar_wait(&bar_k_full[nstage], nphase);
+            mbar_wait(&bar_sfree[g], j & 1);
+            tc_fence_after();
+            issue_s(g, nstage);
+            umma_commit_w(&bar_k_empty[nstage]);
+          }
+          mbar_wait(&bar_p[g], j & 1);
+          mbar_wait(&bar_v_full[stage], phase);
+          tc_fence_after();
+          issue_pv(g, stage, j);
+          umma_commit_w(&bar_v_empty[stage]);
+          stage = nstage;
+          phase = nphase;
+        }
+      } else {
       issue_s(0, 0);
       issue_s(1, 0);
       umma_commit_w(&bar_k_empty[0]);
@@ -1187,6 +1220,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         stage = nstage;
         phase = nphase;
+      }
       }
     }
   } else {
@@ -1244,14 +1278,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tick(1);
       tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
       float* sm = gmax + (j & 1) * 256;
-      sm[hf * 128 + r] = fmaxf(mx0, mx1) * sc;
+      sts_f32(sm + hf * 128 + r, fmaxf(mx0, mx1) * sc);
       if (PE == 17) {
         // the row max is exchanged between exactly two warps (the two column halves of one TMEM lane quadrant): a 64-thread named
         // barrier per warp pair instead of one 256-thread barrier per group lets the pairs drift apart
         asm volatile("bar.sync %0, 64;" ::"r"(5 + g * 4 + qd) : "memory");
       } else if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
-      const float rowmax = fmaxf(sm[r], sm[128 + r]);
+      const float rowmax = fmaxf(lds_f32(sm + r), lds_f32(sm + 128 + r));
       // PE == 16: the exponentials run as ex2.approx.f16x2 (two per MUFU op) on arguments rounded to fp16, whose absolute error grows
       // with |s - m|: keep the stale-max excess below 2 (half-ulp 2^-11 -> 3.4e-4 on the largest probabilities, the size of their own
       // fp16 rounding) instead of 8
@@ -1294,9 +1328,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if ((c + 1) * 32 <= kv_valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a0 = fmaf(__uint_as_float(raw[2 * i]), sc, -m_used), a1 = fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used);
+            float a0, a1;   // s * scale - m for two keys in one FFMA2 (bit-identical to two scalar FMAs)
+            upk2(fma2(pk2u(raw[2 * i], raw[2 * i + 1]), pk2(sc, sc), pk2(-m_used, -m_used)), a0, a1);
             if (PE == 16) pk[i] = ex2_h2(pack_h2(a0, a1));   // one MUFU op -> two probabilities, already packed fp16
-            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) pk[i] = pack_h2(exp2_poly3(a0), exp2_poly3(a1));
+            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) {   // this pair's exponentials on the FMA pipe (packed fp32x2)
+              float e0, e1;
+              exp2_poly3_x2(a0, a1, e0, e1);
+              pk[i] = pack_h2(e0, e1);
+            }
             else pk[i] = pack_h2(fast_exp2(a0), fast_exp2(a1));
           }
         } else {
@@ -1365,7 +1404,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   }
 }
 
-template <int D, int PE, bool TOKEN>
+template <int D, int PE, bool TOKEN, int MW = 1>
 cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const CUtensorMap& mkb, const CUtensorMap& mvbt,
                            const AttnKernelArgs& ka, int L, int heads, int NF, cudaStream_t stream) {
   using C = PPCfg<D>;
@@ -1374,7 +1413,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
   } else {
     static bool attr = false;
     if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<D, PE, TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<D, PE, TOKEN, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
       if (e != cudaSuccess) return e;
       attr = true;
     }
@@ -1384,7 +1423,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       const long long nct = static_cast<long long>(grid.x) * grid.y * grid.z;
       if (cudaMalloc(&kd.dbg, nct * 32 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
       cudaMemsetAsync(kd.dbg, 0, nct * 32 * sizeof(long long), stream);
-      attn_pp_kernel<D, PE, TOKEN><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
+      attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
       cudaStreamSynchronize(stream);
       long long* hb = static_cast<long long*>(malloc(nct * 32 * sizeof(long long)));
       cudaMemcpy(hb, kd.dbg, nct * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1400,7 +1439,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       cudaFree(kd.dbg);
       return cudaGetLastError();
     }
-    attn_pp_kernel<D, PE, TOKEN><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
     return cudaGetLastError();
   }
 }
@@ -1465,7 +1504,7 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   static int use_pt = 1;    // HV_ATTN_PT=0: keep P in shared memory even where it fits in TMEM
   if (!attr) {
     if (const char* pv = getenv("HV_ATTN_POLY")) mode = atoi(pv);
-    if (mode != 0 && mode != 2 && mode != 4 && mode != 13 && mode != 16 && mode != 17 && mode != 31) mode = 0;
+    if (mode != 0 && mode != 2 && mode != 3 && mode != 4 && mode != 13 && mode != 16 && mode != 17 && mode != 31) mode = 0;
     if (const char* pt = getenv("HV_ATTN_PT")) use_pt = atoi(pt);
     const char* ev = getenv("HV_ATTN_WARPS");
     if (ev) nwarps = atoi(ev);
@@ -1502,9 +1541,17 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
   }
   static const int pp_mode = [] { const char* v = getenv("HV_ATTN_PP"); return v ? atoi(v) : 2; }();  // 0 off, 1 token hand-off, 2 free-running groups (default: ~8 % fewer clocks than attn_kernel8 in the network)
-  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 4 || mode == 16 || mode == 17 || mode == 31)) {
+  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 3 || mode == 4 || mode == 16 || mode == 17 || mode == 31)) {
     if (mode == 31) return pp_mode == 2 ? launch_attn_pp<D, 31, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
                                         : launch_attn_pp<D, 31, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    static const int mw_env = [] { const char* v = getenv("HV_ATTN_MW"); return v ? atoi(v) : 2; }();
+    if (mw_env == 2 && mode == 0 && pp_mode == 1) return launch_attn_pp<D, 0, true, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mw_env == 2 && mode == 31) return pp_mode == 1 ? launch_attn_pp<D, 31, true, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
+                                                        : launch_attn_pp<D, 31, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mw_env == 2 && mode == 0) return launch_attn_pp<D, 0, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mw_env == 2 && mode == 4) return launch_attn_pp<D, 4, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mw_env == 2 && mode == 3) return launch_attn_pp<D, 3, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+    if (mw_env == 2 && mode == 2) return launch_attn_pp<D, 2, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (mode == 16) return launch_attn_pp<D, 16, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (mode == 17) return launch_attn_pp<D, 17, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
     if (pp_mode == 2) return launch_attn_pp<D, 0, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);

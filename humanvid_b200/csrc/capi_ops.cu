@@ -37,6 +37,15 @@ int hv_op_conv3x3(const void* X, const void* Wp, void* out, int64_t ldc, int64_t
   return op_conv3x3(H(X), H(Wp), HM(out), ldc, NF, Hh, W, Cin, Cout, stride, ep, ST(stream));
 }
 
+int hv_op_upconv2x2(const void* X, const void* Wp, void* out, int64_t ldc, int64_t NF, int64_t Hh, int64_t W, int64_t Cin, int64_t Cout,
+                    const hv_epilogue* ep, hv_stream_t stream) {
+  return op_upconv2x2(H(X), H(Wp), HM(out), ldc, NF, Hh, W, Cin, Cout, ep, ST(stream));
+}
+int hv_pack_upconv2x2(const void* W, void* out, int64_t Cout, int64_t Cin, hv_stream_t stream) {
+  if (!device_sms()) return HV_ERR_CUDA;
+  CK(launch_pack_upconv2x2(H(W), HM(out), (int)Cout, (int)Cin, device_sms(), ST(stream)), "hv_pack_upconv2x2");
+}
+
 int hv_op_conv3x3_direct(const void* X, const void* W, const void* bias, void* out, int64_t NF, int64_t Hh, int64_t Wd,
                          int64_t Cin, int64_t Cout, int32_t stride, int32_t act, const void* add, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;
@@ -100,6 +109,11 @@ int hv_op_add(const void* A, const void* B, void* out, int64_t n, hv_stream_t st
 int hv_op_pixel_unshuffle(const void* X, void* out, int64_t B, int64_t C, int64_t F, int64_t Hh, int64_t W, int32_t r, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;
   CK(launch_pixel_unshuffle(H(X), HM(out), (int)B, (int)C, (int)F, (int)Hh, (int)W, r, device_sms(), ST(stream)), "hv_op_pixel_unshuffle");
+}
+int hv_op_plucker_unshuffle(const float* K, const float* c2w, void* out, int64_t NF, int64_t Hh, int64_t W, int32_t r, hv_stream_t stream) {
+  if (!device_sms()) return HV_ERR_CUDA;
+  if (!K || !c2w || !out || NF <= 0 || r < 1 || (Hh % r) || (W % r)) { set_error("hv_op_plucker_unshuffle: bad argument"); return HV_ERR_INVALID; }
+  CK(launch_plucker_unshuffle(K, c2w, HM(out), NF, (int)Hh, (int)W, r, device_sms(), ST(stream)), "hv_op_plucker_unshuffle");
 }
 int hv_op_small_linear(const void* X, const void* W, const void* bias, void* out, int64_t M, int64_t N, int64_t K, int32_t act_in, hv_stream_t stream) {
   CK(launch_small_linear(H(X), H(W), H(bias), HM(out), (int)M, (int)N, (int)K, act_in, ST(stream)), "hv_op_small_linear");

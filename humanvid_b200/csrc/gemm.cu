@@ -59,14 +59,21 @@ struct Cfg {
 struct TileCoord {
   int m0;          // linear: first row.   conv: unused
   int n0, y0, x0;  // conv: first frame / output row / output col of the box
+  int py, px;      // A_UPCONV2X2: output parity of this tile (output pixel (2y + py, 2x + px) for source pixel (y, x))
 };
 
 __device__ __forceinline__ TileCoord tile_coord(const GemmProblem& p, int m_blk, int rows_per_tile) {
   TileCoord t;
+  t.py = t.px = 0;
   if (p.a_mode == A_LINEAR) {
     t.m0 = m_blk * rows_per_tile;
     t.n0 = t.y0 = t.x0 = 0;
   } else {
+    if (p.a_mode == A_UPCONV2X2) {   // the four parities of one source box are consecutive tiles (the box stays in L2 for all four)
+      t.py = (m_blk >> 1) & 1;
+      t.px = m_blk & 1;
+      m_blk >>= 2;
+    }
     int xb = m_blk % p.tiles_x;
     int r = m_blk / p.tiles_x;
     int yb = r % p.tiles_y;
@@ -141,7 +148,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + TILE_M - 1) / TILE_M : p.tiles_n * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + TILE_M - 1) / TILE_M : p.tiles_n * p.tiles_y * p.tiles_x * (p.a_mode == A_UPCONV2X2 ? 4 : 1);
   const int n_per_batch = p.b_batch ? (p.b_rows + BLOCK_N - 1) / BLOCK_N : 0;
   const int n_tiles = p.b_batch ? p.b_batch * n_per_batch : (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = m_tiles * n_tiles;
@@ -205,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
         if (++pf_kb == nkb) { pf_kb = 0; pf_tile += gridDim.x; }
       };
-      const bool do_pf = p.pf_dist > 0 && p.a_mode != A_CONV3X3_S2;
+      const bool do_pf = p.pf_dist > 0 && p.a_mode != A_CONV3X3_S2 && p.a_mode != A_UPCONV2X2;
       if (do_pf)
         for (int i = 0; i < p.pf_dist; ++i) pf_step();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -233,6 +240,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const int dy = tap / 3, dx = tap - dy * 3;
             if (p.a_mode == A_CONV3X3) {
               tma_load_4d(sa, &map_a0, &bar_full[stage], cb * BLOCK_K, tc.x0 + dx - 1, tc.y0 + dy - 1, tc.n0);
+            } else if (p.a_mode == A_UPCONV2X2) {
+              // nearest-2x upsample folded into the conv: output (2y+py, 2x+px) reads the 2x2 source pixels (y + a + py - 1, x + b + px - 1)
+              // with the 3x3 taps that land on each pre-summed in the packed weight (tap = 2a + b)
+              const int a = tap >> 1, b = tap & 1;
+              tma_load_4d(sa, &map_a0, &bar_full[stage], cb * BLOCK_K, tc.x0 + b + tc.px - 1, tc.y0 + a + tc.py - 1, tc.n0);
             } else {  // stride 2: memory viewed as (N, H/2, 2, W/2, 2C); input row 2*yo+dy-1, col 2*xo+dx-1
               const int ph = dy == 1 ? 0 : 1, pw = dx == 1 ? 0 : 1;
               tma_load_5d(sa, &map_a0, &bar_full[stage], pw * p.cin + cb * BLOCK_K, tc.x0 - (dx == 0 ? 1 : 0), ph,
@@ -243,7 +255,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             if (p.b_batch)
               tma_load_3d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, (n_blk % n_per_batch) * BLOCK_N, n_blk / n_per_batch);
             else
-              tma_load_2d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+              tma_load_2d(sb, &map_b, &bar_full[stage], kb * BLOCK_K, n_blk * BLOCK_N + (tc.py * 2 + tc.px) * p.b_par_rows);
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
@@ -428,10 +440,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               }
               uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32, one rounding at the store
-                const float h0 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i], h1 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1];
-                const float g0 = __uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i], g1 = __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1];
-                o[i] = pack_h2(h0 * gelu_erf_fast(g0), h1 * gelu_erf_fast(g1));
+              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32 (packed f32x2 math), one rounding at the store
+                const f32x2 hh = add2(pk2u(hraw[c & 1][g * 8 + 2 * i], hraw[c & 1][g * 8 + 2 * i + 1]), pk2(bh[2 * i], bh[2 * i + 1]));
+                const f32x2 gg = add2(pk2u(graw[c & 1][g * 8 + 2 * i], graw[c & 1][g * 8 + 2 * i + 1]), pk2(bg[2 * i], bg[2 * i + 1]));
+                o[i] = geglu2(hh, gg);
               }
               *reinterpret_cast<uint4*>(myrow + (((2 * c + g) ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -479,7 +491,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           const int iy = t2 % p.bh, in = t2 / p.bh;
           const int n = tc.n0 + in, y = tc.y0 + iy, x = tc.x0 + ix;
           row_ok = n < p.NF && y < p.H && x < p.W;
-          row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+          row = p.a_mode == A_UPCONV2X2 ? (static_cast<long long>(n) * 2 * p.H + 2 * y + tc.py) * (2 * p.W) + 2 * x + tc.px
+                                        : (static_cast<long long>(n) * p.H + y) * p.W + x;
         }
         const __half* __restrict__ rv = (e.rowvec != nullptr && row_ok) ? e.rowvec + (row / e.rows_per_group) * e.rowvec_ld : nullptr;
         const __half* __restrict__ res = (e.residual != nullptr && row_ok) ? e.residual + row * e.ldr : nullptr;
@@ -572,10 +585,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
               }
               uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32, one rounding at the store
-                const float h0 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i]) + bh[2 * i], h1 = __uint_as_float(hraw[c & 1][g * 8 + 2 * i + 1]) + bh[2 * i + 1];
-                const float g0 = __uint_as_float(graw[c & 1][g * 8 + 2 * i]) + bg[2 * i], g1 = __uint_as_float(graw[c & 1][g * 8 + 2 * i + 1]) + bg[2 * i + 1];
-                o[i] = pack_h2(h0 * gelu_erf_fast(g0), h1 * gelu_erf_fast(g1));
+              for (int i = 0; i < 4; ++i) {   // hidden * gelu(gate) in fp32 (packed f32x2 math), one rounding at the store
+                const f32x2 hh = add2(pk2u(hraw[c & 1][g * 8 + 2 * i], hraw[c & 1][g * 8 + 2 * i + 1]), pk2(bh[2 * i], bh[2 * i + 1]));
+                const f32x2 gg = add2(pk2u(graw[c & 1][g * 8 + 2 * i], graw[c & 1][g * 8 + 2 * i + 1]), pk2(bg[2 * i], bg[2 * i + 1]));
+                o[i] = geglu2(hh, gg);
               }
               if (row_ok && ocol < e.n_valid) *reinterpret_cast<uint4*>(out + ocol) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -714,7 +727,7 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const CUtensorMap& mo = e.tma_io ? *io_out : a0;
   const CUtensorMap& mr = (e.tma_io && io_res) ? *io_res : mo;
   const int tile_m = BLOCK_M * m_sub;
-  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + tile_m - 1) / tile_m : p.tiles_n * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.a_mode == A_LINEAR ? (p.M + tile_m - 1) / tile_m : p.tiles_n * p.tiles_y * p.tiles_x * (p.a_mode == A_UPCONV2X2 ? 4 : 1);
   const int n_tiles = p.b_batch ? p.b_batch * ((p.b_rows + block_n - 1) / block_n) : (p.N + block_n - 1) / block_n;
   const int tiles = m_tiles * n_tiles;
   if (tiles <= 0 || p.num_k_blocks <= 0) return cudaErrorInvalidValue;

@@ -7,7 +7,7 @@
 
 namespace hv {
 
-enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1, A_CONV3X3_S2 = 2 };
+enum AMode : int { A_LINEAR = 0, A_CONV3X3 = 1, A_CONV3X3_S2 = 2, A_UPCONV2X2 = 3 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
 
 struct GemmEpilogue {
@@ -40,6 +40,7 @@ struct GemmProblem {
   int H = 0, W = 0, NF = 0;        // conv: OUTPUT height / width / frame count
   int bn = 1, bh = 1, bw = 128;    // conv: tile box (bn*bh*bw == 128 or 256 rows per CTA tile)
   int tiles_n = 0, tiles_y = 0, tiles_x = 0;
+  int b_par_rows = 0;              // A_UPCONV2X2: rows of the packed weight per output parity (B is [4 parities][b_par_rows][4 * Cin])
   // batched B operand (V^T = Wv * X^T per frame): B is a 3-D map (K, b_rows, b_batch); output columns of batch n
   // start at n * b_out_stride (a multiple of 8) so every frame's token segment is 16-byte aligned for TMA readers.
   int b_batch = 0, b_rows = 0, b_out_stride = 0;

@@ -92,6 +92,40 @@ __global__ void pixel_unshuffle_kernel(const __half* __restrict__ x, __half* __r
   }
 }
 
+// Plucker-embedding producer (ray_condition, src/dataset/dance_image_h_v_camera.py:88-130) fused with PixelUnshuffle(r): writes the
+// channels-last (B*F, H/r, W/r, 6*r*r) tensor encoder_conv_in reads, straight from the per-frame intrinsics K = (fx, fy, cx, cy) in
+// pixels and camera-to-world matrices (row-major 4x4) -- the (B, 6, F, H, W) embedding (127 MB in fp16 at 24x768x576) is never built.
+//   d = normalize((x + .5 - cx) / fx, (y + .5 - cy) / fy, 1);  rays_d = R d;  rays_o = t;  plucker = [rays_o x rays_d, rays_d]
+// fp32 math like the reference (which runs it on the CPU), one rounding to fp16 (the pipeline's `.to(dtype=fp16)`).
+__global__ void plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ c2w, __half* __restrict__ out, long long total,
+                                         int H, int W, int r) {
+  const int Ho = H / r, Wo = W / r, rr = r * r;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int sub = static_cast<int>(i % rr);           // dy * r + dx: consecutive threads fill consecutive channels of one source plane
+    long long t = i / rr;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const long long n = t / Ho;                          // b * F + f
+    const int y = yo * r + sub / r, x = xo * r + sub % r;
+    const float* k = K + n * 4;
+    const float* m = c2w + n * 16;
+    float dx = (static_cast<float>(x) + 0.5f - k[2]) / k[0];
+    float dy = (static_cast<float>(y) + 0.5f - k[3]) / k[1];
+    float dz = 1.0f;
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= nrm; dy /= nrm; dz /= nrm;
+    const float rx = dx * m[0] + dy * m[1] + dz * m[2];
+    const float ry = dx * m[4] + dy * m[5] + dz * m[6];
+    const float rz = dx * m[8] + dy * m[9] + dz * m[10];
+    const float ox = m[3], oy = m[7], oz = m[11];
+    const float v[6] = {oy * rz - oz * ry, oz * rx - ox * rz, ox * ry - oy * rx, rx, ry, rz};
+    __half* dst = out + ((n * Ho + yo) * Wo + xo) * (6LL * rr) + sub;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dst[c * rr] = __float2half_rn(v[c]);
+  }
+}
+
 // y[m][n] = fp16( sum_k act(x[m][k]) * w[n][k] + bias[n] ); one warp per output element (M is tiny).
 __global__ void small_linear_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                                     __half* __restrict__ out, int M, int N, int K, int act_in) {
@@ -224,6 +258,27 @@ __global__ void dbg_gemm_kernel(const __half* __restrict__ a, long long lda, con
   out[i] = acc;
 }
 
+// (Cout, Cin, 3, 3) -> [parity py*2+px][Cout][(2a+b)*Cin + c]: the 3x3 taps of a conv applied to a nearest-2x upsampled image, summed
+// (fp32, one rounding) onto the 2x2 source pixels they read.  Output row 2y+py reads source rows {y-1, y, y} (py = 0) or {y, y, y+1}
+// (py = 1) for dy = 0, 1, 2: a = 0 collects dy in {0} / {0, 1}, a = 1 collects {1, 2} / {2}; columns alike.
+__global__ void pack_upconv2x2_kernel(const __half* __restrict__ w, __half* __restrict__ out, long long total, int Cout, int Cin) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cin);
+    long long t = i / Cin;
+    const int tap = static_cast<int>(t % 4);
+    t /= 4;
+    const int co = static_cast<int>(t % Cout);
+    const int par = static_cast<int>(t / Cout);
+    const int py = par >> 1, px = par & 1, a = tap >> 1, b = tap & 1;
+    const int dy0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), dy1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int dx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), dx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    float s = 0.f;
+    for (int dy = dy0; dy <= dy1; ++dy)
+      for (int dx = dx0; dx <= dx1; ++dx) s += __half2float(w[((static_cast<long long>(co) * Cin + c) * 3 + dy) * 3 + dx]);
+    out[i] = __float2half_rn(s);
+  }
+}
+
 }  // namespace
 
 #define HV_LAUNCH_CHECK() return cudaGetLastError()
@@ -260,6 +315,11 @@ cudaError_t launch_pixel_unshuffle(const __half* x, __half* out, int B, int C, i
   pixel_unshuffle_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(x, out, total, B, C, F, H, W, r);
   HV_LAUNCH_CHECK();
 }
+cudaError_t launch_plucker_unshuffle(const float* K, const float* c2w, __half* out, long long NF, int H, int W, int r, int num_sms, cudaStream_t s) {
+  const long long total = NF * H * W;
+  plucker_unshuffle_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(K, c2w, out, total, H, W, r);
+  HV_LAUNCH_CHECK();
+}
 cudaError_t launch_small_linear(const __half* x, const __half* w, const __half* bias, __half* out, int M, int N, int K, int act_in,
                                 cudaStream_t s) {
   const long long warps = static_cast<long long>(M) * N;
@@ -288,6 +348,11 @@ cudaError_t launch_conv3x3_direct_padded(const __half* x, const __half* w, const
 cudaError_t launch_pack_conv3x3(const __half* w, __half* out, int Cout, int Cin, int Cout_pad, int Cin_pad, int num_sms, cudaStream_t s) {
   const long long total = static_cast<long long>(Cout_pad) * 9 * Cin_pad;
   pack_conv3x3_kernel<__half><<<blocks_for(total, num_sms), kThreads, 0, s>>>(w, out, total, Cout, Cin, Cin_pad);
+  HV_LAUNCH_CHECK();
+}
+cudaError_t launch_pack_upconv2x2(const __half* w, __half* out, int Cout, int Cin, int num_sms, cudaStream_t s) {
+  const long long total = 16LL * Cout * Cin;
+  pack_upconv2x2_kernel<<<blocks_for(total, num_sms), kThreads, 0, s>>>(w, out, total, Cout, Cin);
   HV_LAUNCH_CHECK();
 }
 cudaError_t launch_pack_geglu(const __half* w, __half* out, int rows, int K, int num_sms, cudaStream_t s) {

@@ -299,6 +299,22 @@ struct hv_model {
     if (bias) c.bias = vec(pfx + ".bias", cout, c.cout_pad);
     return c;
   }
+  // Upsample3D's conv packed for op_upconv2x2: [4 parities][cout][4 * cin]
+  Conv3 upconv(const std::string& pfx, int cout, int cin) {
+    const Raw& r = get(pfx + ".weight");
+    if (r.shape.size() != 4 || r.shape[0] != cout || r.shape[1] != cin || r.shape[2] != 3 || r.shape[3] != 3)
+      fail(HV_ERR_INVALID, "weight '%s.weight' is not (%d,%d,3,3)", pfx.c_str(), cout, cin);
+    if ((cin % 64) || (cout % 8)) fail(HV_ERR_INVALID, "upsampler conv '%s': %d -> %d channels must be multiples of 64 / 8", pfx.c_str(), cin, cout);
+    Conv3 c;
+    c.cin = c.cin_pad = cin;
+    c.cout = c.cout_pad = cout;
+    c.w.rows = 4LL * cout;
+    c.w.cols = 4LL * cin;
+    c.w.p = dmalloc(c.w.rows * c.w.cols);
+    ck(launch_pack_upconv2x2(r.p, c.w.p, cout, cin, sms, st), "pack upconv2x2");
+    c.bias = vec(pfx + ".bias", cout);
+    return c;
+  }
   ConvDirect conv_direct(const std::string& pfx, int cout, int cin) {
     ConvDirect c;
     c.w = get(pfx + ".weight").p;
@@ -442,7 +458,7 @@ struct hv_model {
         if (mm) u.mm.push_back(motion(p + ".motion_modules." + std::to_string(j), c));
       }
       u.has_up = i < 3;
-      if (u.has_up) u.up = conv3(p + ".upsamplers.0.conv", c, c);
+      if (u.has_up) u.up = upconv(p + ".upsamplers.0.conv", c, c);
       prev = c;
     }
     if (cfg.kind == HV_KIND_UNET3D) {   // the reference ("writer") 2-D UNet has its post-process removed (unet_2d_condition.py:1295-1299)
@@ -652,7 +668,7 @@ struct hv_model {
         if (flags & HV_FLAG_COND_ONLY) {
           if (w.bank_B < B) fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld < forward batch %d", w.name.c_str(), (long long)w.bank_B, B);
           item0 = w.bank_B - B;
-        } else if (w.bank_B != B) {
+        } else if (w.bank_B != B && !ar.dry) {   // (a planning pass only sizes the workspace; it does not know the flags of the forward to come)
           fail(HV_ERR_INVALID, "reference bank of '%s' has batch %lld, forward batch is %d", w.name.c_str(), (long long)w.bank_B, B);
         }
         const __half* bank = w.bank + item0 * w.bank_L * C;
@@ -822,9 +838,16 @@ struct hv_model {
         if (!u.mm.empty()) { h = motion_fwd(u.mm[j], h, B, F); tap(pb + ".motion_modules." + std::to_string(j), h); }
       }
       if (u.has_up) {
-        Tens big = alloc_act(h.NF, 2 * h.H, 2 * h.W, h.C);
-        if (!ar.dry) { launches += 1; ck(launch_upsample2x(h.p, big.p, h.NF, h.H, h.W, h.C, sms, st), "upsample"); }
-        h = op_conv3(big, u.up, 1, nullptr, 1, HV_ACT_NONE, nullptr);
+        // Upsample3D (resnet.py:68-71): nearest 2x + 3x3 conv as four 2x2 convs of the source -- the 4x tensor is never materialised
+        Tens big = alloc_act(h.NF, 2 * h.H, 2 * h.W, u.up.cout);
+        if (!ar.dry) {
+          hv_epilogue ep{};
+          ep.bias = u.up.bias;
+          launches += 1;
+          Timed tm(this, CAT_CONV, 2.0 * big.rows() * u.up.cout * 4.0 * u.up.cin, "upconv2x2", big.rows(), u.up.cout, 4LL * u.up.cin);
+          ckop(op_upconv2x2(h.p, u.up.w.p, big.p, u.up.cout, h.NF, h.H, h.W, u.up.cin, u.up.cout, &ep, st), "upsampler conv");
+        }
+        h = big;
         tap(pb + ".upsamplers.0", h);
       }
     }
@@ -857,12 +880,20 @@ struct hv_model {
     if (!ar.dry) { launches += 1; ck(launch_nhwc_to_ncfhw(h.p, h.C, outp, B, cfg.pg_out_channels, F, h.H, h.W, st), "pose output layout"); }
   }
 
-  void camera_forward(const __half* plucker, __half* outp, int B, int F, int H, int W) {
+  void camera_forward(const __half* plucker, __half* outp, int B, int F, int H, int W, const float* rays_K = nullptr, const float* rays_c2w = nullptr) {
     const int r = cfg.cam_downscale, NF = B * F, C = cfg.cam_channels;
     if ((H % r) || (W % r)) fail(HV_ERR_INVALID, "plucker map %dx%d must be a multiple of %d", H, W, r);
     const int cin0 = cfg.cam_cin / (r * r);
     Tens u = alloc_act(NF, H / r, W / r, cfg.cam_cin);
-    if (!ar.dry) { launches += 1; ck(launch_pixel_unshuffle(plucker, u.p, B, cin0, F, H, W, r, sms, st), "pixel unshuffle"); }
+    if (!ar.dry) {
+      launches += 1;
+      if (rays_K != nullptr) {   // Plucker embedding generated in place of the unshuffle's gather
+        if (cin0 != 6) fail(HV_ERR_INVALID, "the Plucker producer makes 6 channels, encoder expects %d", cin0);
+        ck(launch_plucker_unshuffle(rays_K, rays_c2w, u.p, NF, H, W, r, sms, st), "plucker unshuffle");
+      } else {
+        ck(launch_pixel_unshuffle(plucker, u.p, B, cin0, F, H, W, r, sms, st), "pixel unshuffle");
+      }
+    }
     Tens x = op_conv3(u, cam_in, 1, nullptr, 1, HV_ACT_NONE, nullptr);
     for (int j = 0; j < cfg.cam_nums_rb; ++j) {
       // ResnetBlock (pose_adaptor.py:102-135, sk=True, ksize=1): x = block2(relu(block1(x))) + x
@@ -1050,11 +1081,11 @@ int hv_clear_ref_banks(hv_handle h) {
   return HV_OK;
 }
 
-static size_t measure(hv_model* h, int B, int F, int H, int W) {
+static size_t measure(hv_model* h, int B, int F, int H, int W, uint32_t flags = HV_FLAG_CFG) {
   h->begin(nullptr, 0, true, nullptr);
   if (h->cfg.kind == HV_KIND_UNET3D || h->cfg.kind == HV_KIND_UNET2D_REF) {
     static __half dummy;
-    h->unet_forward(&dummy, 0, &dummy, h->cfg.kind == HV_KIND_UNET3D ? &dummy : nullptr, &dummy, B, F, H, W, HV_FLAG_CFG);
+    h->unet_forward(&dummy, 0, &dummy, h->cfg.kind == HV_KIND_UNET3D ? &dummy : nullptr, &dummy, B, F, H, W, flags);
   } else if (h->cfg.kind == HV_KIND_POSE_GUIDER) {
     h->pose_guider_forward(nullptr, nullptr, B, F, H, W);
   } else {
@@ -1125,7 +1156,8 @@ int hv_unet3d_forward(hv_handle h, const void* sample, int64_t timestep, const v
   if (!h || !sample || !ehs || !out) return HV_ERR_INVALID;
   HV_GUARD(h, {
     if (!h->finalized || h->cfg.kind != HV_KIND_UNET3D) fail(HV_ERR_STATE, "handle is not a finalized UNet3D");
-    const size_t need = measure(h, B, F, height, width);
+    if ((flags & HV_FLAG_UNCOND_ONLY) && (flags & HV_FLAG_COND_ONLY)) fail(HV_ERR_INVALID, "HV_FLAG_UNCOND_ONLY and HV_FLAG_COND_ONLY are exclusive");
+    const size_t need = measure(h, B, F, height, width, flags);
     size_t have = 0;
     void* ws = get_ws(h, workspace, ws_bytes, need, &have);
     h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
@@ -1181,6 +1213,19 @@ int hv_camera_encoder_forward(hv_handle h, const void* plucker, void* out, int32
     void* ws = get_ws(h, workspace, ws_bytes, need, &have);
     h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
     h->camera_forward(static_cast<const __half*>(plucker), static_cast<__half*>(out), B, F, H, W);
+  });
+}
+
+int hv_camera_encoder_forward_rays(hv_handle h, const float* intrinsics, const float* c2w, void* out, int32_t B, int32_t F, int32_t H, int32_t W,
+                                   void* workspace, size_t ws_bytes, hv_stream_t stream) {
+  if (!h || !intrinsics || !c2w || !out) return HV_ERR_INVALID;
+  HV_GUARD(h, {
+    if (!h->finalized || h->cfg.kind != HV_KIND_CAMERA_ENCODER) fail(HV_ERR_STATE, "handle is not a finalized CameraPoseEncoder");
+    const size_t need = measure(h, B, F, H, W);
+    size_t have = 0;
+    void* ws = get_ws(h, workspace, ws_bytes, need, &have);
+    h->begin(ws, have, false, static_cast<cudaStream_t>(stream));
+    h->camera_forward(nullptr, static_cast<__half*>(out), B, F, H, W, intrinsics, c2w);
   });
 }
 

@@ -82,7 +82,8 @@ static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
 // 256-row CTA tiles (two UMMA sub-tiles sharing one B stage) when K is large enough to amortise the then
 // single-buffered accumulator's epilogue and there is enough work to fill the machine.
 static int pick_m_sub(int64_t rows, int64_t N, int bn, int64_t K, int sms) {
-  if (K < 2816) return 1;  // 3x3 convs (K >= 2880) and the widest linears only: below that the exposed epilogue costs more than the L2 traffic saved
+  static const int64_t min_k = [] { const char* v = getenv("HV_GEMM_MT2_MINK"); return v ? atoll(v) : 2816LL; }();
+  if (K < min_k) return 1;  // 3x3 convs (K >= 2880) and the widest linears only: below that the exposed epilogue costs more than the L2 traffic saved
   const int64_t tiles2 = ((rows + 255) / 256) * ((N + bn - 1) / bn);
   return tiles2 >= sms ? 2 : 1;
 }
@@ -212,6 +213,46 @@ int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int6
   fill_epilogue(e, ep, out, ldc, Cout);
   cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream, m_sub);
   if (err != cudaSuccess) return cuda_fail(err, "hv_op_conv3x3 launch");
+  return HV_OK;
+}
+
+// Nearest-2x upsample + 3x3 conv (Upsample3D, resnet.py:68-71 + :49) as four 2x2 convolutions of the SOURCE tensor, one per output
+// parity: the 4x larger upsampled tensor is never written or read and the conv does 4/9 of the multiply-adds.
+int op_upconv2x2(const __half* X, const __half* Wp, __half* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                 const hv_epilogue* ep, cudaStream_t stream) {
+  const int sms = device_sms();
+  if (!sms) return HV_ERR_CUDA;
+  if ((Cin % 64) || (Cout % 8) || (ldc % 8) || NF <= 0 || H <= 0 || W <= 0 || (ep && (ep->residual || ep->rowvec || ep->geglu))) {
+    set_error("hv_op_upconv2x2: bad shape NF=%lld H=%lld W=%lld Cin=%lld Cout=%lld (or unsupported epilogue)", (long long)NF, (long long)H, (long long)W,
+              (long long)Cin, (long long)Cout);
+    return HV_ERR_INVALID;
+  }
+  GemmProblem p;
+  p.a_mode = A_UPCONV2X2;
+  p.N = static_cast<int>(Cout);
+  p.cin_blocks = static_cast<int>(Cin / 64);
+  p.cin = static_cast<int>(Cin);
+  p.num_k_blocks = 4 * p.cin_blocks;
+  p.H = static_cast<int>(H);     // tile space = SOURCE pixels; the epilogue scatters to (2y + py, 2x + px)
+  p.W = static_cast<int>(W);
+  p.NF = static_cast<int>(NF);
+  p.b_par_rows = static_cast<int>(Cout);
+  const int64_t rows = NF * H * W;
+  const int bn = pick_block_n(Cout, (4 * rows + 127) / 128, false, sms);
+  if (Cout % bn) { set_error("hv_op_upconv2x2: Cout=%lld must be a multiple of the %d-column tile", (long long)Cout, bn); return HV_ERR_INVALID; }
+  const int m_sub = pick_m_sub(4 * rows, Cout, bn, 4 * Cin, sms);
+  choose_conv_box(p.NF, p.H, p.W, &p.bn, &p.bh, &p.bw, 128 * m_sub);
+  p.tiles_n = (p.NF + p.bn - 1) / p.bn;
+  p.tiles_y = (p.H + p.bh - 1) / p.bh;
+  p.tiles_x = (p.W + p.bw - 1) / p.bw;
+  p.M = p.NF * p.H * p.W;
+  CUtensorMap ma, mb;
+  if (!make_map_nhwc(&ma, X, NF, H, W, Cin, p.bn, p.bh, p.bw)) { set_error("hv_op_upconv2x2 X map: %s", tma_last_error()); return HV_ERR_TMA; }
+  if (!make_map_2d(&mb, Wp, 4 * Cout, 4 * Cin, 4 * Cin, bn)) { set_error("hv_op_upconv2x2 W map: %s", tma_last_error()); return HV_ERR_TMA; }
+  GemmEpilogue e;
+  fill_epilogue(e, ep, out, ldc, Cout);
+  cudaError_t err = launch_gemm(ma, ma, mb, p, e, bn, sms, stream, m_sub);
+  if (err != cudaSuccess) return cuda_fail(err, "hv_op_upconv2x2 launch");
   return HV_OK;
 }
 

@@ -22,4 +22,8 @@ int op_gemm_batched_b(const __half* A, int64_t lda, const __half* X, int64_t ldx
 int op_conv3x3(const __half* X, const __half* Wp, __half* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin,
                int64_t Cout, int stride, const hv_epilogue* ep, cudaStream_t stream);
 
+// out (NF, 2H, 2W, Cout) = conv3x3(nearest_upsample_2x(X (NF, H, W, Cin))) + bias; Wp from launch_pack_upconv2x2: [4][Cout][4 * Cin].
+int op_upconv2x2(const __half* X, const __half* Wp, __half* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                 const hv_epilogue* ep, cudaStream_t stream);
+
 }  // namespace hv

@@ -303,6 +303,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// explicit shared-state-space accesses (a pointer that went through uintptr_t alignment arithmetic compiles to generic LD.E / ST.E)
+__device__ __forceinline__ float lds_f32(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(float* p, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory"); }
+
 // ---------------------------------------------------------------- misc
 // a += lo(h2), b += hi(h2): fp32 accumulators plus the two halves of a packed fp16 pair, one FHADD each (mixed-precision
 // add.f32.f16, sm_100a) -- no separate half -> float conversion.
@@ -346,6 +354,65 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaxf(x, 0.f) - fabsf(q);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot).  The epilogues and the softmax are
+// issue-bound, not FLOP-bound, so halving the instruction count of their fp32 math is worth more than anything else there.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// hidden * gelu_erf(gate) for two (hidden, gate) pairs at once, same A&S 7.1.26 form as gelu_erf_fast; returns the packed fp16 pair.
+__device__ __forceinline__ uint32_t geglu2(f32x2 h, f32x2 g) {
+  float g0, g1;
+  upk2(g, g0, g1);
+  const float a0 = fabsf(g0), a1 = fabsf(g1);
+  const f32x2 ax = pk2(a0, a1);
+  float d0, d1;
+  upk2(fma2(pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), ax, pk2(1.0f, 1.0f)), d0, d1);
+  const f32x2 t = pk2(fast_rcp(d0), fast_rcp(d1));
+  f32x2 poly = fma2(pk2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, pk2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  poly = fma2(poly, t, pk2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  poly = fma2(poly, t, pk2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  poly = fma2(poly, t, pk2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  float e0, e1;
+  upk2(mul2(mul2(g, g), pk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), e0, e1);
+  const f32x2 e = pk2(fast_exp2(e0), fast_exp2(e1));                    // exp(-x^2 / 2)
+  float q0, q1;
+  upk2(mul2(mul2(poly, t), mul2(e, ax)), q0, q1);                       // 0.5 |x| erfc(|x| / sqrt2) >= 0
+  const f32x2 r = pk2(fmaxf(g0, 0.f) - q0, fmaxf(g1, 0.f) - q1);        // relu(x) - 0.5 |x| erfc(|x|/sqrt2) = x Phi(x)
+  float o0, o1;
+  upk2(mul2(h, r), o0, o1);
+  return pack_h2(o0, o1);
+}
+
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], relative error 7.5e-5: a third of the fp16
 // half-ulp of the probabilities it produces).  Used for a fraction of the softmax exponentials so that the 16-lane
 // MUFU pipe is not the only unit doing them.
@@ -357,6 +424,22 @@ __device__ __forceinline__ float exp2_poly3(float x) {
   p = fmaf(p, f, 0.6932609677f);
   p = fmaf(p, f, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(fi) << 23));
+}
+
+// the same for two arguments at once on packed fp32x2 (FFMA2) -- 12 issue slots for two exponentials instead of 18
+__device__ __forceinline__ void exp2_poly3_x2(float x0, float x1, float& y0, float& y1) {
+  const f32x2 x = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const f32x2 magic = pk2(12582912.f, 12582912.f);
+  const f32x2 fi = add2(x, magic);
+  const f32x2 f = fma2(add2(fi, pk2(-12582912.f, -12582912.f)), pk2(-1.f, -1.f), x);
+  f32x2 p = fma2(f, pk2(0.0551716685f, 0.0551716685f), pk2(0.2426111251f, 0.2426111251f));
+  p = fma2(p, f, pk2(0.6932609677f, 0.6932609677f));
+  p = fma2(p, f, pk2(0.9999280572f, 0.9999280572f));
+  float p0, p1, i0, i1;
+  upk2(p, p0, p1);
+  upk2(fi, i0, i1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(i0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(i1) << 23));
 }
 
 }  // namespace hv

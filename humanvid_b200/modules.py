@@ -876,6 +876,27 @@ class CameraPoseEncoder(_NativeNet):
         return [out.to(x.dtype) if x.dtype != torch.float16 else out]
 
 
+    @torch.no_grad()
+    def forward_cameras(self, intrinsics: torch.Tensor, c2w: torch.Tensor, height: int, width: int) -> List[torch.Tensor]:
+        """``forward(ray_condition(intrinsics, c2w, height, width) as (b, 6, f, h, w))`` without building the embedding
+        (SURVEY 8f-3): intrinsics (b, f, 4) in pixels, c2w (b, f, 4, 4), see humanvid_b200.camera.relative_cameras."""
+        if intrinsics.dim() != 3 or intrinsics.shape[-1] != 4 or c2w.shape != (*intrinsics.shape[:2], 4, 4):
+            raise ValueError("intrinsics must be (b, f, 4) and c2w (b, f, 4, 4)")
+        B, F = intrinsics.shape[:2]
+        r = self._cfg["downscale"]
+        if self._cfg["cin"] != 6 * r * r:
+            raise ValueError("the Plucker producer feeds a 6-channel encoder")
+        h = self._sync_native()
+        dev = self.device
+        K = intrinsics.to(dev, torch.float32).contiguous()
+        M = c2w.to(dev, torch.float32).contiguous()
+        out = torch.empty((B * F, self._cfg["c"], height // r, width // r), device=dev, dtype=torch.float16)
+        self._reserve(h, B, F, height, width)
+        N.check(N.lib().hv_camera_encoder_forward_rays(h, N.ptr(K), N.ptr(M), N.ptr(out), N.i32(B), N.i32(F), N.i32(height), N.i32(width), None,
+                                                       C.c_size_t(0), N.stream()), h)
+        return [out.to(self.dtype) if self.dtype != torch.float16 else out]
+
+
 # --------------------------------------------------------------------------------------------- ReferenceAttentionControl (reader)
 class ReferenceAttentionControl:
     """src/models/mutual_self_attention.py for the native UNets: same constructor keywords / ``update(writer)`` / ``clear()``.

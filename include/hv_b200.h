@@ -113,6 +113,12 @@ int hv_pose_guider_forward(hv_handle h, const void* conditioning, void* out, int
 int hv_camera_encoder_forward(hv_handle h, const void* plucker, void* out, int32_t B, int32_t F, int32_t H, int32_t W,
                               void* workspace, size_t ws_bytes, hv_stream_t stream);
 
+/* The same encoder fed by the cameras themselves instead of the 6-channel Plucker image: intrinsics DEVICE fp32
+ * (B, F, 4) = (fx, fy, cx, cy) in pixels, c2w DEVICE fp32 (B, F, 4, 4) relative camera-to-world poses -- what
+ * scripts/pose2vid.py:66-80 hands to ray_condition.  The embedding is generated inside the PixelUnshuffle producer. */
+int hv_camera_encoder_forward_rays(hv_handle h, const float* intrinsics, const float* c2w, void* out, int32_t B, int32_t F, int32_t H,
+                                   int32_t W, void* workspace, size_t ws_bytes, hv_stream_t stream);
+
 /* Debug taps (per-layer error ladder, profiles/): the activation leaving the i-th block of the UNet forward (conv_in, every
  * resnet / transformer / motion module / down- / up-sampler, in execution order) is copied to dst[i] as channels-last fp16
  * (NF, H, W, C).  hv_debug_tap_count plans the forward at this shape and returns the number of taps; hv_debug_tap_info

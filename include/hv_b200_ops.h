@@ -67,6 +67,15 @@ int hv_op_gemm_batched_b(const void* A, int64_t lda, const void* X, int64_t ldx,
                          int64_t rows, int64_t out_stride, int64_t K, const void* rowbias /* fp16 [M] added to row m, or NULL */,
                          hv_stream_t stream);
 
+/* Upsample3D (src/models/resnet.py:29-88): nearest 2x upsample followed by the 3x3 convolution, WITHOUT materialising the upsampled
+ * tensor: every output parity (2y+py, 2x+px) is a 2x2 convolution of the source whose weights are sums of the 3x3 taps that land on
+ * the same source pixel (4/9 of the multiply-adds; the summed weights are rounded to fp16 once, at packing).
+ * X (NF, H, W, Cin) -> out (NF, 2H, 2W, Cout) given as [rows][ldc]; Wp = hv_pack_upconv2x2(W (Cout, Cin, 3, 3)) : [4][Cout][4 * Cin].
+ * Epilogue: bias only.  Cin % 64 == 0; Cout a multiple of the 128/160/256-column tile the GEMM picks (320, 640, 1280 are). */
+int hv_op_upconv2x2(const void* X, const void* Wp, void* out, int64_t ldc, int64_t NF, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                    const hv_epilogue* ep, hv_stream_t stream);
+int hv_pack_upconv2x2(const void* W, void* out, int64_t Cout, int64_t Cin, hv_stream_t stream);
+
 /* 3x3 convolution, padding 1, stride 1 or 2, over channels-last X (NF, H, W, Cin) -> out (NF, Ho, Wo, Cout) given as
  * a [rows][ldc] matrix.  Wp is the packed weight [Cout][9 * Cin] with k = (ky*3 + kx) * Cin + c (see hv_pack_conv3x3).
  * Cin must be a multiple of 64; stride 2 needs even H and W. */
@@ -117,6 +126,11 @@ int hv_op_upsample2x(const void* X, void* out, int64_t NF, int64_t H, int64_t W,
 int hv_op_add(const void* A, const void* B, void* out, int64_t n, hv_stream_t stream);
 int hv_op_pixel_unshuffle(const void* X, void* out, int64_t B, int64_t C, int64_t F, int64_t H, int64_t W, int32_t r,
                           hv_stream_t stream);
+/* Plucker-embedding producer on the device (Camera + ray_condition, src/dataset/dance_image_h_v_camera.py:17-130; called from
+ * scripts/pose2vid.py:52-84) fused with CameraPoseEncoder's PixelUnshuffle(r) (pose_adaptor.py:222,233-236):
+ * K: DEVICE fp32 [NF][4] = (fx, fy, cx, cy) in pixels; c2w: DEVICE fp32 [NF][16] row-major camera-to-world (relative poses);
+ * out: channels-last fp16 (NF, H/r, W/r, 6*r*r) with channel = c*r*r + dy*r + dx, i.e. pixel_unshuffle(plucker (NF, 6, H, W)). */
+int hv_op_plucker_unshuffle(const float* K, const float* c2w, void* out, int64_t NF, int64_t H, int64_t W, int32_t r, hv_stream_t stream);
 /* y[M][N] = act_in(x[M][K]) * W[N][K]^T + bias, tiny M (time embedding, cross-attention collapse); fp32 math,
  * fp16 rounding of the result. act_in: hv_act applied to x first. */
 int hv_op_small_linear(const void* X, const void* W, const void* bias, void* out, int64_t M, int64_t N, int64_t K,

@@ -108,13 +108,65 @@ def main():
     y32 = run_oracle(ora, names, x.float(), a.timestep, ehs.float(), pose.float(), visit32)
     rows.append(("conv_out (network output)", tuple(y32.shape), rel(yn, y32), rel(y16, y32), rel(yn, y16)))
 
+    # ---- isolated per-block error: the oracle's block in fp32 applied to the NATIVE block's own input (the native taps of its
+    # predecessors), against the native block's output -- "identical inputs, per tensor" (north_star), free of the error the input
+    # already carried.  (Reference banks change the attention inputs, so this column is produced for the bank-free run only.)
+    iso = {}
+    if not a.banks:
+        B = 2
+
+        def to_ncfhw(t):  # (B*F, H, W, C) fp16 -> (B, C, F, H, W) fp32
+            nf, hh, ww, c = t.shape
+            return t.reshape(B, nf // B, hh, ww, c).permute(0, 4, 1, 2, 3).float().contiguous()
+
+        mods = dict(ora.named_modules())
+        with torch.no_grad():
+            tt = torch.tensor([a.timestep], device=dev).expand(B)
+            emb = ora.time_embedding(O.timestep_sincos(tt, ora.conv_in.out_channels).float())
+            ehs32 = ehs.float()
+            iso["conv_in"] = rel(native["conv_in"], to_nhwc(ora.conv_in(x.float()) + pose.float()))
+            # the skip stack of the forward (unet_3d.py:486-506): conv_in, then every down layer's last module, then the block's downsampler
+            skips = ["conv_in"]
+            for n in names:
+                if n.startswith("down_blocks"):
+                    blk, kind, idx = n.rsplit(".", 2)
+                    if kind == "downsamplers":
+                        skips.append(n)
+                    elif kind == "resnets":
+                        skips.append(n)                      # provisional: replaced by the layer's later modules below
+                    else:
+                        skips[-1] = n                        # attentions.j / motion_modules.j follow resnets.j of the same layer
+            prev = "conv_in"
+            for n in names[1:]:
+                h_in = to_ncfhw(native[prev])
+                kind = n.split(".")[-2]
+                if n.startswith("up_blocks") and kind == "resnets":
+                    h_in = torch.cat([h_in, to_ncfhw(native[skips.pop()])], dim=1)
+                m = mods[n]
+                if kind == "resnets":
+                    out = m(h_in, emb)
+                elif kind == "attentions":
+                    out = m(h_in, ehs32)
+                elif kind == "upsamplers":
+                    out = m(h_in, None)
+                else:   # motion_modules, downsamplers
+                    out = m(h_in)
+                iso[n] = rel(native[n], to_nhwc(out))
+                del out, h_in
+                prev = n
+            assert not skips, skips
+
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:
         f.write(f"# error ladder: latent {H}x{W}, {F} frames, CFG batch 2, widths {chs}, banks={a.banks}, timestep {a.timestep}, seed-7 synthetic init\n")
         f.write("# relative L2 error of the activation leaving each block (channels-last (NF,H,W,C))\n")
-        f.write(f"# {'block':38s} {'shape':>22s} {'native/fp32':>12s} {'eager16/fp32':>13s} {'native/eager16':>15s}\n")
+        f.write("# isolated = the oracle's block in fp32 applied to the native block's OWN input (native taps) vs the native block's output\n")
+        f.write(f"# {'block':38s} {'shape':>22s} {'native/fp32':>12s} {'eager16/fp32':>13s} {'native/eager16':>15s} {'isolated':>10s}\n")
         for n, s, e1, e2, e3 in rows:
-            f.write(f"{n:40s} {str(s):>22s} {e1:12.3e} {e2:13.3e} {e3:15.3e}\n")
+            f.write(f"{n:40s} {str(s):>22s} {e1:12.3e} {e2:13.3e} {e3:15.3e} " + (f"{iso[n]:10.3e}" if n in iso else f"{'-':>10s}") + "\n")
+        if iso:
+            wi = max(iso.items(), key=lambda kv: kv[1])
+            f.write(f"# max isolated per-block error: {wi[1]:.3e} at {wi[0]}\n")
         worst = max(rows, key=lambda r: r[2])
         f.write(f"# max native/fp32 over the ladder: {worst[2]:.3e} at {worst[0]}; network output: native/fp32 {rows[-1][2]:.3e}, "
                 f"eager16/fp32 {rows[-1][3]:.3e}, native/eager16 {rows[-1][4]:.3e}\n")

@@ -64,13 +64,16 @@ def test_config5_window_shape_with_banks():
         ctl.clear()
     torch.cuda.synchronize()
     e_ref, e_nat, e_pair = rel(y16, y32), rel(yn, y32), rel(yn, y16)
+    e_un, e_co = rel(y_un, y32[:1]), rel(y_co, y32[1:])
     report(f"config5 window (2,4,24,72,128) + banks: fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}; "
-           f"unit split vs CFG batch: uncond {rel(y_un, yn[:1]):.1e}, cond {rel(y_co, yn[1:]):.1e}")
+           f"one-half units vs fp32: uncond {e_un:.2e}, cond {e_co:.2e}; units vs CFG batch: {rel(y_un, yn[:1]):.1e} / {rel(y_co, yn[1:]):.1e}")
     assert torch.isfinite(yn).all()
-    assert e_nat <= 1.25 * e_ref
-    assert e_nat <= 2e-3
+    assert e_nat <= e_ref and e_nat <= 1.6e-3             # measured 1.46e-3 vs 1.78e-3 for the reference's own fp16 path
     assert torch.equal(yn[:1], plain[:1]) and rel(yn[1:], plain[1:]) > 1e-2
-    assert rel(y_un, yn[:1]) <= 5e-4 and rel(y_co, yn[1:]) <= 5e-4
+    # the (window x CFG-half) units of the multi-GPU split are forwards of the same quality (bitwise equal to the halves of the CFG batch:
+    # every per-frame reduction order is independent of the batch size)
+    assert e_un <= e_ref and e_co <= e_ref
+    assert torch.equal(y_un, yn[:1]) and torch.equal(y_co, yn[1:])
 
 
 def test_pose_guider_and_camera_encoder_full_resolution():

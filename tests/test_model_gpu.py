@@ -225,6 +225,43 @@ def test_pose_guider_and_camera_encoder_golden():
     assert rel(y, g["y"].cuda()) < 3e-3
 
 
+def test_camera_encoder_from_cameras_plucker_on_device():
+    """the Plucker embedding generated on the GPU inside the encoder's PixelUnshuffle producer, from the intrinsics / relative
+    poses of a shipped camera trajectory (tests/golden/plucker.pt: rows of data/test_set/camera_test_set.zip and the reference's own
+    Camera + ray_condition output), against (a) the golden embedding and (b) the encoder fed with that embedding."""
+    import ctypes as C
+
+    import torch.nn.functional as F
+
+    from humanvid_b200 import _native as N
+    from humanvid_b200 import camera as Cm
+
+    g = torch.load(os.path.join(GOLD, "plucker.pt"), weights_only=False)
+    img = tuple(g["img_size"])                               # (W, H) = (48, 64)
+    cams = [Cm.Camera(r, "test", img) for r in g["rows"]]
+    K, c2w = Cm.relative_cameras(cams, 0, list(range(1, 9)), img)
+    Fr, H, W = 8, img[1], img[0]
+    gold = g["y"].cuda()                                     # (1, 8, 6, 64, 48) fp16, the reference's ray_condition output
+    un = torch.zeros(Fr, H // 8, W // 8, 384, device="cuda", dtype=torch.half)
+    Kd, Md = K.cuda().contiguous(), c2w.cuda().contiguous()   # (kept referenced: the launch is asynchronous)
+    N.check(N.lib().hv_op_plucker_unshuffle(N.ptr(Kd), N.ptr(Md), N.ptr(un), N.i64(Fr), N.i64(H), N.i64(W), N.i32(8), N.stream()))
+    ref_un = F.pixel_unshuffle(gold[0], 8).permute(0, 2, 3, 1).contiguous()
+    torch.cuda.synchronize()
+    e_embed = rel(un, ref_un)
+    o = O.synthetic_init(O.CameraPoseEncoder().eval(), seed=13)
+    cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                               temporal_position_encoding_max_len=24)
+    cam.load_state_dict(o.state_dict())
+    cam = cam.to("cuda", torch.float16)
+    y_img = cam(gold.transpose(1, 2).contiguous())[0]        # (1, 6, 8, H, W) like scripts/pose2vid.py:285 hands it to the pipeline
+    y_cam = cam.forward_cameras(K, c2w, H, W)[0]
+    torch.cuda.synchronize()
+    print(f"plucker on device: embedding vs reference golden {e_embed:.2e}; encoder output vs embedding-fed encoder {rel(y_cam, y_img):.2e}")
+    assert (un.float() - ref_un.float()).abs().max() <= 2e-3 and e_embed < 3e-4      # fp32 ray arithmetic, differences of one fp16 ulp
+    assert y_cam.shape == y_img.shape and rel(y_cam, y_img) < 1e-3
+
+
 def test_pose_guider_config2_shape_vs_oracle_fp16():
     o = O.synthetic_init(O.PoseGuider().eval(), seed=3).half().cuda()
     pg = hv.PoseGuider(320, block_out_channels=(16, 32, 96, 256))

@@ -114,6 +114,23 @@ def test_conv3x3(NF, H, W, Cin, Cout, stride):
     assert rel(out, ref) < 1e-3, rel(out, ref)
 
 
+@pytest.mark.parametrize("NF,H,W,Cin,Cout", [(2, 12, 9, 1280, 1280), (3, 24, 18, 640, 640), (2, 48, 36, 320, 320), (1, 5, 7, 64, 128), (48, 12, 9, 1280, 1280)])
+def test_upconv2x2_is_upsample_then_conv(NF, H, W, Cin, Cout):
+    """Upsample3D (resnet.py:68-71, :49): F.interpolate(nearest, 2x) + 3x3 conv, computed as four 2x2 convs of the source."""
+    x = dev(NF, H, W, Cin, seed=25)
+    w = dev(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=26)
+    bias = dev(Cout, seed=27)
+    wp = torch.empty(4 * Cout, 4 * Cin, device="cuda", dtype=torch.half)
+    check(lib().hv_pack_upconv2x2(ptr(w), ptr(wp), i64(Cout), i64(Cin), stream()))
+    out = torch.zeros(NF * 4 * H * W, Cout, device="cuda", dtype=torch.half)
+    ep = Epilogue(bias=ptr(bias).value)
+    check(lib().hv_op_upconv2x2(ptr(x), ptr(wp), ptr(out), i64(Cout), i64(NF), i64(H), i64(W), i64(Cin), i64(Cout), C.byref(ep), stream()))
+    up = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-3, rel(out, ref)
+
+
 def test_conv3x3_direct_small_channels():
     NF, H, W, Cin, Cout = 2, 32, 24, 3, 16
     x, w, b = dev(NF, H, W, Cin, seed=30), dev(Cout, Cin, 3, 3, scale=0.2, seed=31), dev(Cout, seed=32)
