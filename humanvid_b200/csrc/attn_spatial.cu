@@ -25,12 +25,12 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tma.h"
+#include "tuning.h"
 
 namespace hv {
 
 namespace {
 
-constexpr int ATT_THREADS = 192;
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per tile
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is rescaled only when the row max grows by more than 2^8
@@ -66,314 +66,6 @@ struct AttnKernelArgs {
   float scale_log2;
   long long* dbg;   // PE == 31 only: per-CTA accumulated clock64() spans of the pipeline phases (16 slots per CTA)
 };
-
-template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, ACfg<D>::kMinBlocks)
-attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-            const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
-            const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
-  using C = ACfg<D>;
-  constexpr int DP = C::kDpad, DV = C::kDv;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sP = sQ + C::kQBytes;
-  uint8_t* sKV = sP + C::kPBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::kStages * C::kStageBytes);
-  uint64_t* bar_q = bars;
-  uint64_t* bar_p = bars + 1;
-  uint64_t* bar_pv = bars + 2;
-  uint64_t* bar_s = bars + 3;        // [2]: S half h (keys 64h..64h+63 of the tile) is in TMEM
-  uint64_t* bar_sfree = bars + 5;    // [2]: the softmax warps have read S half h (128 arrivals)
-  uint64_t* bar_kv_full = bars + 7;
-  uint64_t* bar_kv_empty = bars + 7 + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * C::kStages);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QT;
-  const int h = blockIdx.y;
-  const int n = blockIdx.z;
-  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
-  const int Ts = (a.L + KT - 1) / KT;
-  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
-  const int bidx = n / a.F;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_pv, 1);
-    for (int hh = 0; hh < 2; ++hh) {
-      mbar_init(&bar_s[hh], 1);
-      mbar_init(&bar_sfree[hh], 128);
-    }
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&bar_kv_full[s], 1);
-      mbar_init(&bar_kv_empty[s], 1);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_k);
-    tma_prefetch_desc(&map_vt);
-  }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;          // 128 columns: S tile
-  const uint32_t tmem_o = tmem_base + 128;    // DV columns: O accumulator (column D = softmax denominator)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, C::kQBytes);
-#pragma unroll
-      for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sQ + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
-        uint8_t* sK = sKV + stage * C::kStageBytes;
-        uint8_t* sV = sK + C::kKBytes;
-        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
-        const bool self = j < Ts;
-        const CUtensorMap* mk = self ? &map_k : &map_kb;
-        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
-        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;                    // K rows
-        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;   // V^T columns (16B aligned)
-#pragma unroll
-        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
-        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
-        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      // S is produced in two 64-key halves (UMMA 128x64xdpad each) so that, with two K/V stages, the next tile's scores
-      // are already in TMEM while the softmax warps still work on the current tile: they never wait for the tensor pipe.
-      constexpr uint32_t idesc_sh = umma_idesc_f16(QT, KT / 2);
-      auto issue_s_half = [&](int stage, int hh) {
-        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes) + hh * (KT / 2) * 128;
-#pragma unroll
-        for (int ks = 0; ks < DP / 16; ++ks) {
-          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
-          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
-          umma_f16_ss(tmem_s + hh * (KT / 2), ad, bd, idesc_sh, ks != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_s[hh]);
-      };
-      auto issue_pv = [&](int stage, int j) {
-        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
-#pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk) {
-          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
-          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
-          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);   // O accumulates across key tiles in TMEM
-        }
-        umma_commit(bar_pv);
-        umma_commit(&bar_kv_empty[stage]);
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv_full[0], 0);
-      tc_fence_after();
-      issue_s_half(0, 0);
-      issue_s_half(0, 1);
-      for (int j = 0; j < T; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == C::kStages) { nstage = 0; nphase ^= 1; }
-        if constexpr (C::kStages >= 2) {
-          if (j + 1 < T) {
-            mbar_wait(&bar_kv_full[nstage], nphase);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              mbar_wait(&bar_sfree[hh], j & 1);
-              tc_fence_after();
-              issue_s_half(nstage, hh);
-            }
-          }
-          mbar_wait(bar_p, j & 1);
-          tc_fence_after();
-          issue_pv(stage, j);
-        } else {
-          // one K/V stage only (d = 160): the next K tile can only land after this tile's P V released the stage
-          mbar_wait(bar_p, j & 1);
-          tc_fence_after();
-          issue_pv(stage, j);
-          if (j + 1 < T) {
-            mbar_wait(&bar_kv_full[nstage], nphase);
-            tc_fence_after();
-            issue_s_half(nstage, 0);   // S halves were released before bar_p was completed
-            issue_s_half(nstage, 1);
-          }
-        }
-        stage = nstage;
-        phase = nphase;
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax: one query row per thread
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;                 // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    float m_used = -INFINITY;                     // the (possibly stale) row max the accumulated O and P are relative to
-    uint8_t* prow = sP + r * 128;
-    const int sw = r & 7;
-    const float sc = a.scale_log2;
-
-    // Rescale of this row's O accumulator (and of the P chunks of the current tile already written) when the row max
-    // grows by more than the threshold.  Warp-collective because tcgen05.ld/st are; lanes that do not grow use alpha = 1.
-    auto rescale = [&](float alpha, int chunks_done) {
-#pragma unroll
-      for (int c = 0; c < DV / 16; ++c) {
-        uint32_t t16[16];
-        tmem_ld16(tmem_o + lane_off + c * 16, t16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
-        tmem_st16(tmem_o + lane_off + c * 16, t16);
-      }
-      tmem_st_wait();
-      const __half2 a2 = __float2half2_rn(alpha);
-      for (int cc = 0; cc < chunks_done; ++cc) {
-        uint8_t* chunk = prow + (cc >> 1) * (QT * 128);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4* ptr = reinterpret_cast<uint4*>(chunk + ((((cc & 1) * 4 + u) ^ sw) << 4));
-          uint4 v = *ptr;
-          __half2* hp = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hp[i] = __hmul2(hp[i], a2);
-          *ptr = v;
-        }
-      }
-    };
-
-    for (int j = 0; j < T; ++j) {
-      const bool self = j < Ts;
-      const int kv_valid = self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT);
-      mbar_wait(&bar_s[0], j & 1);
-      tc_fence_after();
-      bool pv_pending = j > 0;   // P smem and the O accumulator are ours again only once the previous P V has completed;
-                                 // that wait is deferred to the first point that needs it (first P store / a rescale)
-      uint32_t raw[2][32];
-      if (j == 0) {
-        mbar_wait(&bar_s[1], 0);
-        tc_fence_after();
-        // first tile: one extra sweep over S to seed the row max (later tiles only check for growth, chunk by chunk)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        tmem_ld32(tmem_s + lane_off, raw[0]);
-#pragma unroll
-        for (int c = 0; c < KT / 32; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < KT / 32) tmem_ld32(tmem_s + lane_off + (c + 1) * 32, raw[(c + 1) & 1]);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
-            if (c * 32 + i + 1 < kv_valid) mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][i + 1]));
-          }
-        }
-        m_used = fmaxf(mx0, mx1) * sc;
-      }
-      tmem_ld32(tmem_s + lane_off, raw[0]);
-#pragma unroll
-      for (int c = 0; c < KT / 32; ++c) {
-        tmem_ld_wait();
-        if (c & 1) {   // both chunks of S half (c >> 1) are in registers: hand the half back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&bar_sfree[c >> 1]);
-        }
-        if (c == 1 && j > 0) {   // (on the first tile both halves were already awaited for the max sweep)
-          mbar_wait(&bar_s[1], j & 1);
-          tc_fence_after();
-        }
-        if (c + 1 < KT / 32) tmem_ld32(tmem_s + lane_off + (c + 1) * 32, raw[(c + 1) & 1]);
-        const bool full = (c + 1) * 32 <= kv_valid;
-        if (j > 0) {
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
-              mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][i + 1]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][i]));
-          }
-          const float cm = fmaxf(mx0, mx1) * sc;
-          const bool grow = cm > m_used + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, grow)) {
-            const float m_new = grow ? cm : m_used;
-            if (pv_pending) { mbar_wait(bar_pv, (j - 1) & 1); tc_fence_after(); pv_pending = false; }
-            rescale(grow ? fast_exp2(m_used - m_new) : 1.0f, c);
-            m_used = m_new;
-          }
-        }
-        uint32_t pk[16];
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i + 1]), sc, -m_used)));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c0 = c * 32 + 2 * i;
-            const float p0 = c0 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i]), sc, -m_used)) : 0.f;       // keys past the
-            const float p1 = c0 + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[c & 1][2 * i + 1]), sc, -m_used)) : 0.f; // segment end: p = 0
-            pk[i] = pack_h2(p0, p1);
-          }
-        }
-        if (pv_pending) { mbar_wait(bar_pv, (j - 1) & 1); tc_fence_after(); pv_pending = false; }
-        uint8_t* chunk = prow + (c >> 1) * (QT * 128);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(chunk + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(bar_p);
-    }
-    // epilogue: O / denominator
-    mbar_wait(bar_pv, (T - 1) & 1);
-    tc_fence_after();
-    float o[DV];
-#pragma unroll
-    for (int c = 0; c < DV / 16; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(tmem_o + lane_off + c * 16, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw[i]);
-    }
-    tc_fence_before();
-    if (q0 + r < a.L) {
-      const float inv = 1.f / o[D];
-      __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
-#pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        uint4 u;
-        u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-        u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-        u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-        u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + c * 8) = u;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Variant with EIGHT softmax warps (two threads per query row, one per 64-key half of the tile).  ncu on the 4-warp
@@ -743,285 +435,6 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Variant with SIXTEEN softmax warps, one CTA per SM: four threads per query row, each owning 32 keys of a tile, so the
-// thread keeps its scores in registers (one TMEM read per tile) and hands the S buffer back to the MMA warp at once.
-// S and P are double-buffered (TMEM 2 x 128 columns + O; shared memory 2 x 32 KB), K/V tiles go through a 3-4 stage ring:
-// the tensor pipe works one key tile ahead and the softmax warps only ever wait for each other (row-max exchange).
-constexpr int ATT16_THREADS = 576;
-
-template <int D>
-struct A16Cfg {
-  using B = ACfg<D>;
-  static constexpr int kPBuf = 2 * QT * 128;                          // one P buffer (two 64-key chunks)
-  static constexpr int kFixed = B::kQBytes + 2 * kPBuf + 256 + 4096 + 1024;
-  static constexpr int kFit = (227 * 1024 - kFixed) / B::kStageBytes;
-  static constexpr int kStages = kFit > 4 ? 4 : (kFit < 1 ? 1 : kFit);
-  static constexpr int kSmemBytes = kFixed + kStages * B::kStageBytes;
-};
-
-template <int D>
-__global__ void __launch_bounds__(ATT16_THREADS, 1)
-attn_kernel16(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-              const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
-              const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
-  using C = ACfg<D>;
-  using C16 = A16Cfg<D>;
-  constexpr int DP = C::kDpad, DV = C::kDv, NST = C16::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sP = sQ + C::kQBytes;                   // [2] buffers
-  uint8_t* sKV = sP + 2 * C16::kPBuf;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * C::kStageBytes);
-  uint64_t* bar_q = bars;
-  uint64_t* bar_s = bars + 1;        // [2] S buffer b holds a fresh tile
-  uint64_t* bar_sfree = bars + 3;    // [2] all 512 softmax threads have read S buffer b
-  uint64_t* bar_p = bars + 5;        // [2] P buffer b written (512 arrivals)
-  uint64_t* bar_pv = bars + 7;       // [2] the P V of a tile with parity b has completed
-  uint64_t* bar_kv_full = bars + 9;
-  uint64_t* bar_kv_empty = bars + 9 + NST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * NST);
-  float* smax = reinterpret_cast<float*>(bars + 32);   // [2 (tile parity)][4 (key quarter)][128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QT;
-  const int h = blockIdx.y;
-  const int n = blockIdx.z;
-  const bool use_bank = a.Lb > 0 && n >= a.nf_nobank;
-  const int Ts = (a.L + KT - 1) / KT;
-  const int T = Ts + (use_bank ? (a.Lb + KT - 1) / KT : 0);
-  const int bidx = n / a.F;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_s[b], 1);
-      mbar_init(&bar_sfree[b], 512);
-      mbar_init(&bar_p[b], 512);
-      mbar_init(&bar_pv[b], 1);
-    }
-    for (int s = 0; s < NST; ++s) {
-      mbar_init(&bar_kv_full[s], 1);
-      mbar_init(&bar_kv_empty[s], 1);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_k);
-    tma_prefetch_desc(&map_vt);
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;   // S buffers at columns 0 and 128
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, C::kQBytes);
-#pragma unroll
-      for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sQ + kc * QT * 128, &map_q, bar_q, h * DP + kc * 64, n * a.L + q0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(&bar_kv_empty[stage], phase ^ 1);
-        uint8_t* sK = sKV + stage * C::kStageBytes;
-        uint8_t* sV = sK + C::kKBytes;
-        mbar_arrive_expect_tx(&bar_kv_full[stage], C::kStageBytes);
-        const bool self = j < Ts;
-        const CUtensorMap* mk = self ? &map_k : &map_kb;
-        const CUtensorMap* mv = self ? &map_vt : &map_vbt;
-        const int tok = self ? n * a.L + j * KT : bidx * a.Lb + (j - Ts) * KT;
-        const int vcol = self ? n * a.vt_stride + j * KT : bidx * a.vbt_stride + (j - Ts) * KT;
-#pragma unroll
-        for (int kc = 0; kc < C::kKC; ++kc) tma_load_2d(sK + kc * KT * 128, mk, &bar_kv_full[stage], h * DP + kc * 64, tok);
-        tma_load_2d(sV, mv, &bar_kv_full[stage], vcol, h * DV);
-        tma_load_2d(sV + C::kVChunk, mv, &bar_kv_full[stage], vcol + 64, h * DV);
-        if (++stage == NST) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
-      const uint32_t aQ = smem_u32(sQ);
-      auto issue_s = [&](int stage, int b) {
-        const uint32_t aK = smem_u32(sKV + stage * C::kStageBytes);
-#pragma unroll
-        for (int ks = 0; ks < DP / 16; ++ks) {
-          const uint64_t ad = umma_desc_k_sw128(aQ + (ks / 4) * QT * 128) + 2 * (ks % 4);
-          const uint64_t bd = umma_desc_k_sw128(aK + (ks / 4) * KT * 128) + 2 * (ks % 4);
-          umma_f16_ss(tmem_base + b * 128, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_s[b]);
-      };
-      auto issue_pv = [&](int stage, int j) {
-        const uint32_t aP = smem_u32(sP + (j & 1) * C16::kPBuf);
-        const uint32_t aV = smem_u32(sKV + stage * C::kStageBytes + C::kKBytes);
-#pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk) {
-          const uint64_t ad = umma_desc_k_sw128(aP + (kk / 4) * QT * 128) + 2 * (kk % 4);
-          const uint64_t bd = umma_desc_k_sw128(aV + (kk / 4) * C::kVChunk) + 2 * (kk % 4);
-          umma_f16_ss(tmem_o, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_pv[j & 1]);
-        umma_commit(&bar_kv_empty[stage]);
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      for (int j = 0; j < T; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == NST) { nstage = 0; nphase ^= 1; }
-        if constexpr (NST >= 2) {
-          if (j + 1 < T) {
-            const int b = (j + 1) & 1;
-            mbar_wait(&bar_kv_full[nstage], nphase);
-            mbar_wait(&bar_sfree[b], ((((j + 1) >> 1) & 1) ^ 1));   // previous tile on this S buffer (if any) has been read
-            tc_fence_after();
-            issue_s(nstage, b);
-          }
-          mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
-          tc_fence_after();
-          issue_pv(stage, j);
-        } else {
-          mbar_wait(&bar_p[j & 1], (j >> 1) & 1);
-          tc_fence_after();
-          issue_pv(stage, j);
-          if (j + 1 < T) {
-            const int b = (j + 1) & 1;
-            mbar_wait(&bar_kv_full[nstage], nphase);
-            mbar_wait(&bar_sfree[b], ((((j + 1) >> 1) & 1) ^ 1));
-            tc_fence_after();
-            issue_s(nstage, b);
-          }
-        }
-        stage = nstage;
-        phase = nphase;
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax: four threads per query row
-    const int qd = warp & 3;
-    const int cq = (warp - 2) >> 2;               // which 32-key quarter of every tile this thread owns
-    const int r = qd * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    float m_used = -INFINITY;
-    const int sw = r & 7;
-    const float sc = a.scale_log2;
-
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      const bool self = j < Ts;
-      const int kv_valid = (self ? min(KT, a.L - j * KT) : min(KT, a.Lb - (j - Ts) * KT)) - cq * 32;   // valid keys in my quarter (may be <= 0)
-      mbar_wait(&bar_s[b], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + lane_off + b * 128 + cq * 32, raw);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&bar_sfree[b]);                 // scores are in registers: the S buffer can be overwritten
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-      if (kv_valid >= 32) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(raw[i + 1]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(raw[i]));
-      }
-      float* sm = smax + b * 512;
-      sm[cq * 128 + r] = fmaxf(mx0, mx1) * sc;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      const float rowmax = fmaxf(fmaxf(sm[r], sm[128 + r]), fmaxf(sm[256 + r], sm[384 + r]));
-      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in the four threads of the row
-      const float m_new = grow ? rowmax : m_used;
-      if (j > 0 && cq == 0 && __any_sync(0xffffffffu, grow)) {
-        mbar_wait(&bar_pv[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O holds tiles 0..j-1
-        tc_fence_after();
-        const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
-#pragma unroll
-        for (int c = 0; c < DV / 16; ++c) {
-          uint32_t t16[16];
-          tmem_ld16(tmem_o + lane_off + c * 16, t16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(t16[i]) * alpha);
-          tmem_st16(tmem_o + lane_off + c * 16, t16);
-        }
-        tmem_st_wait();
-      }
-      m_used = m_new;
-      uint32_t pk[16];
-      if (kv_valid >= 32) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_h2(fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)), fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = 2 * i < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i]), sc, -m_used)) : 0.f;
-          const float p1 = 2 * i + 1 < kv_valid ? fast_exp2(fmaf(__uint_as_float(raw[2 * i + 1]), sc, -m_used)) : 0.f;
-          pk[i] = pack_h2(p0, p1);
-        }
-      }
-      if (j >= 2) {   // P buffer b was last read by the P V of tile j-2
-        mbar_wait(&bar_pv[b], ((j - 2) >> 1) & 1);
-      }
-      uint8_t* prow = sP + b * C16::kPBuf + (cq >> 1) * (QT * 128) + r * 128;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        *reinterpret_cast<uint4*>(prow + ((((cq & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&bar_p[b]);
-    }
-    // epilogue: O / denominator; the four threads of a row write interleaved 8-column groups
-    mbar_wait(&bar_pv[(T - 1) & 1], ((T - 1) >> 1) & 1);
-    tc_fence_after();
-    float o[DV];
-#pragma unroll
-    for (int c = 0; c < DV / 16; ++c) {
-      uint32_t raw16[16];
-      tmem_ld16(tmem_o + lane_off + c * 16, raw16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[c * 16 + i] = __uint_as_float(raw16[i]);
-    }
-    tc_fence_before();
-    if (q0 + r < a.L) {
-      const float inv = 1.f / o[D];
-      __half* dst = a.out + (static_cast<long long>(n) * a.L + q0 + r) * a.ldo + h * D;
-#pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        if ((c & 3) == cq) {
-          uint4 u;
-          u.x = pack_h2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-          u.y = pack_h2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-          u.z = pack_h2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-          u.w = pack_h2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + c * 8) = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // "Ping-pong" variant for head dims < 48: ONE CTA per SM works on TWO 128-query tiles (groups A and B) of the same
 // (frame, head) against one shared K/V stream.  What the per-phase clocks of attn_kernel8 showed: a tcgen05.mma of this size
 // costs ~50 clocks to issue and ~300 to drain whatever its N, so S = Q K^T (6 MMAs) and P V (8 MMAs) put ~1100 clocks of
@@ -1279,18 +692,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
       float* sm = gmax + (j & 1) * 256;
       sts_f32(sm + hf * 128 + r, fmaxf(mx0, mx1) * sc);
-      if (PE == 17) {
-        // the row max is exchanged between exactly two warps (the two column halves of one TMEM lane quadrant): a 64-thread named
-        // barrier per warp pair instead of one 256-thread barrier per group lets the pairs drift apart
-        asm volatile("bar.sync %0, 64;" ::"r"(5 + g * 4 + qd) : "memory");
-      } else if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 2, 256;" ::: "memory");
       const float rowmax = fmaxf(lds_f32(sm + r), lds_f32(sm + 128 + r));
-      // PE == 16: the exponentials run as ex2.approx.f16x2 (two per MUFU op) on arguments rounded to fp16, whose absolute error grows
-      // with |s - m|: keep the stale-max excess below 2 (half-ulp 2^-11 -> 3.4e-4 on the largest probabilities, the size of their own
-      // fp16 rounding) instead of 8
-      constexpr float kThr = PE == 16 ? 2.0f : kRescaleThreshold;
-      const bool grow = rowmax > m_used + kThr;   // identical in both threads of the row
+      const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
       const float m_new = grow ? rowmax : m_used;
       tick(2);
       tmem_ld_wait();
@@ -1330,8 +735,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int i = 0; i < 16; ++i) {
             float a0, a1;   // s * scale - m for two keys in one FFMA2 (bit-identical to two scalar FMAs)
             upk2(fma2(pk2u(raw[2 * i], raw[2 * i + 1]), pk2(sc, sc), pk2(-m_used, -m_used)), a0, a1);
-            if (PE == 16) pk[i] = ex2_h2(pack_h2(a0, a1));   // one MUFU op -> two probabilities, already packed fp16
-            else if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) {   // this pair's exponentials on the FMA pipe (packed fp32x2)
+            if (PE > 0 && PE < 10 && (i % (PE > 0 ? PE : 1)) == PE - 1) {   // this pair's exponentials on the FMA pipe (packed fp32x2)
               float e0, e1;
               exp2_poly3_x2(a0, a1, e0, e1);
               pk[i] = pack_h2(e0, e1);
@@ -1498,27 +902,6 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
     if (!make_map_2d(&mvbt, a.vbt, static_cast<long long>(a.heads) * C::kDv, static_cast<long long>(B) * a.vbt_stride, a.ldvbt, C::kDv))
       return cudaErrorInvalidValue;
   }
-  static bool attr = false;
-  static int nwarps = 8;
-  static int mode = 0;      // HV_ATTN_POLY: 0 (default), 2 / 4 = polynomial exp2 on every 2nd / 4th pair, 13 / 31 = timing experiments
-  static int use_pt = 1;    // HV_ATTN_PT=0: keep P in shared memory even where it fits in TMEM
-  if (!attr) {
-    if (const char* pv = getenv("HV_ATTN_POLY")) mode = atoi(pv);
-    if (mode != 0 && mode != 2 && mode != 3 && mode != 4 && mode != 13 && mode != 16 && mode != 17 && mode != 31) mode = 0;
-    if (const char* pt = getenv("HV_ATTN_PT")) use_pt = atoi(pt);
-    const char* ev = getenv("HV_ATTN_WARPS");
-    if (ev) nwarps = atoi(ev);
-    if (nwarps != 4 && nwarps != 8 && nwarps != 16) nwarps = 8;
-    {
-      cudaError_t e16 = cudaFuncSetAttribute(attn_kernel16<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, A16Cfg<D>::kSmemBytes);
-      if (e16 != cudaSuccess) return e16;
-    }
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
   AttnKernelArgs ka;
   ka.out = a.out;
   ka.ldo = a.ldo;
@@ -1532,45 +915,31 @@ cudaError_t launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   ka.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   ka.dbg = nullptr;
   dim3 grid((a.L + QT - 1) / QT, a.heads, a.NF);
-  if (nwarps == 16) {
-    attn_kernel16<D><<<grid, ATT16_THREADS, A16Cfg<D>::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
-    return cudaGetLastError();
-  }
-  if (nwarps == 4) {
-    attn_kernel<D><<<grid, ATT_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
-    return cudaGetLastError();
-  }
-  static const int pp_mode = [] { const char* v = getenv("HV_ATTN_PP"); return v ? atoi(v) : 2; }();  // 0 off, 1 token hand-off, 2 free-running groups (default: ~8 % fewer clocks than attn_kernel8 in the network)
-  if (PPCfg<D>::kFits && pp_mode != 0 && a.L > QT && (mode == 0 || mode == 2 || mode == 3 || mode == 4 || mode == 16 || mode == 17 || mode == 31)) {
-    if (mode == 31) return pp_mode == 2 ? launch_attn_pp<D, 31, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
-                                        : launch_attn_pp<D, 31, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    static const int mw_env = [] { const char* v = getenv("HV_ATTN_MW"); return v ? atoi(v) : 2; }();
-    if (mw_env == 2 && mode == 0 && pp_mode == 1) return launch_attn_pp<D, 0, true, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mw_env == 2 && mode == 31) return pp_mode == 1 ? launch_attn_pp<D, 31, true, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
-                                                        : launch_attn_pp<D, 31, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mw_env == 2 && mode == 0) return launch_attn_pp<D, 0, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mw_env == 2 && mode == 4) return launch_attn_pp<D, 4, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mw_env == 2 && mode == 3) return launch_attn_pp<D, 3, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mw_env == 2 && mode == 2) return launch_attn_pp<D, 2, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mode == 16) return launch_attn_pp<D, 16, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mode == 17) return launch_attn_pp<D, 17, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (pp_mode == 2) return launch_attn_pp<D, 0, false>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mode == 4) return launch_attn_pp<D, 4, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    if (mode == 2) return launch_attn_pp<D, 2, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-    return launch_attn_pp<D, 0, true>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
-  }
   constexpr bool kCanPT = 128 + 64 + C::kDv <= 256;
-  const bool pt = kCanPT && use_pt != 0;
-#define HV_ATT8(PE_)                                                                                                   \
-  (pt ? launch_attn8<D, PE_, kCanPT>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream) : launch_attn8<D, PE_, false>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream))
-  switch (mode) {
-    case 2: return HV_ATT8(2);
-    case 4: return HV_ATT8(4);
-    case 13: return HV_ATT8(13);
-    case 31: return HV_ATT8(31);
-    default: return HV_ATT8(0);
+#ifdef HV_TUNING
+  // A/B experiments (build with -DHV_TUNING, see humanvid_b200/build.py): HV_ATTN_POLY = 0 / 2 / 3 / 4 (every n-th exponential pair on the
+  // FMA pipe) or 31 (blocking run that prints per-phase clocks); HV_ATTN_MW = 1 / 2 MMA-issuing warps; HV_ATTN_PP = 0 (one query tile per
+  // CTA) / 1 (token hand-off between the groups) / 2 (free-running groups).  The release build has exactly one path per head dim.
+  static const int mode = [] { const char* v = getenv("HV_ATTN_POLY"); return v ? atoi(v) : 4; }();
+  static const int mw = [] { const char* v = getenv("HV_ATTN_MW"); return v ? atoi(v) : 2; }();
+  static const int pp = [] { const char* v = getenv("HV_ATTN_PP"); return v ? atoi(v) : 2; }();
+  if (PPCfg<D>::kFits && pp != 0 && a.L > QT) {
+#define HV_PP(PE_, TOK_, MW_) return launch_attn_pp<D, PE_, TOK_, MW_>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream)
+#define HV_PP_MODE(TOK_, MW_) \
+    switch (mode) { case 0: HV_PP(0, TOK_, MW_); case 2: HV_PP(2, TOK_, MW_); case 3: HV_PP(3, TOK_, MW_); case 31: HV_PP(31, TOK_, MW_); default: HV_PP(4, TOK_, MW_); }
+    if (pp == 1 && mw == 2) { HV_PP_MODE(true, 2) }
+    if (pp == 1) { HV_PP_MODE(true, 1) }
+    if (mw == 2) { HV_PP_MODE(false, 2) }
+    HV_PP_MODE(false, 1)
+#undef HV_PP_MODE
+#undef HV_PP
   }
-#undef HV_ATT8
+  if (mode == 31) return launch_attn8<D, 31, kCanPT>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream);
+#else
+  // d < 48 (level 0, d = 40): two query tiles per CTA, one MMA issuer per tile, every 4th exponential pair on the FMA pipe
+  if (PPCfg<D>::kFits && a.L > QT) return launch_attn_pp<D, 4, false, 2>(mq, mk, mvt, mkb, mvbt, ka, a.L, a.heads, a.NF, stream);
+#endif
+  return launch_attn8<D, 0, kCanPT>(grid, mq, mk, mvt, mkb, mvbt, ka, a.L, stream);
 }
 
 }  // namespace

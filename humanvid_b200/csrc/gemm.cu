@@ -18,6 +18,7 @@
 
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "tuning.h"
 
 namespace hv {
 
@@ -708,7 +709,7 @@ static cudaError_t launch_bst(const CUtensorMap& a0, const CUtensorMap& a1, cons
 }
 
 bool gemm_wants_cluster(int64_t M, int64_t N, int block_n, int m_sub, bool batched_b) {
-  static const int env = [] { const char* v = getenv("HV_GEMM_CLUSTER"); return v ? atoi(v) : 0; }();
+  static const int env = static_cast<int>(tune_env("HV_GEMM_CLUSTER", 0));
   if (!env || m_sub != 1 || batched_b) return false;
   const int64_t n_tiles = (N + block_n - 1) / block_n, m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   return (n_tiles % 2) == 0 && m_tiles * n_tiles >= 2 * 148;   // pairs exist and the persistent grid is full
@@ -717,7 +718,7 @@ bool gemm_wants_cluster(int64_t M, int64_t N, int block_n, int m_sub, bool batch
 cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmProblem& p_in,
                         const GemmEpilogue& e_in, int block_n, int num_sms, cudaStream_t stream, int m_sub, const CUtensorMap* io_out,
                         const CUtensorMap* io_res) {
-  static const int pf_env = [] { const char* v = getenv("HV_GEMM_PF"); return v ? atoi(v) : 0; }();  // experiment, off: the extra TMA requests cost more than the latency they hide
+  static const int pf_env = static_cast<int>(tune_env("HV_GEMM_PF", 0));  // experiment, off: the extra TMA requests cost more than the latency they hide
   GemmProblem p = p_in;
   p.pf_dist = pf_env;
   if (p.cluster && !(m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && gemm_wants_cluster(p.M, p.N, block_n, m_sub, false)))
@@ -735,7 +736,7 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   if (e.geglu && block_n != 256) return cudaErrorInvalidValue;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.cluster) grid &= ~1;
-  static const int bst_env = [] { const char* v = getenv("HV_GEMM_BST"); return v ? atoi(v) : 1; }();
+  static const int bst_env = static_cast<int>(tune_env("HV_GEMM_BST", 1));
   if (bst_env && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && n_tiles <= num_sms) {
     cudaError_t r = cudaErrorNotSupported;
     if (block_n == 256) r = launch_bst<256>(a0, a1, b, mo, mr, p, e, m_tiles, n_tiles, num_sms, stream);

@@ -7,6 +7,7 @@
 #include "gemm.cuh"
 #include "kernels.h"
 #include "tma.h"
+#include "tuning.h"
 
 namespace hv {
 
@@ -64,8 +65,8 @@ static void fill_epilogue(GemmEpilogue& e, const hv_epilogue* ep, __half* out, i
 // ties go to the wider tile (fewer A re-reads, better UMMA smem ratio) unless that leaves SMs idle.
 static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
   if (geglu) return 256;
-  if (const char* ev = getenv("HV_GEMM_BN")) {  // tuning/debug override
-    const int v = atoi(ev);
+  {
+    const int v = static_cast<int>(tune_env("HV_GEMM_BN", 0));  // tuning build only
     if (v == 128 || v == 160 || v == 256) return v;
   }
   const int cand[3] = {256, 160, 128};
@@ -82,7 +83,7 @@ static int pick_block_n(int64_t N, int64_t m_tiles, bool geglu, int sms) {
 // 256-row CTA tiles (two UMMA sub-tiles sharing one B stage) when K is large enough to amortise the then
 // single-buffered accumulator's epilogue and there is enough work to fill the machine.
 static int pick_m_sub(int64_t rows, int64_t N, int bn, int64_t K, int sms) {
-  static const int64_t min_k = [] { const char* v = getenv("HV_GEMM_MT2_MINK"); return v ? atoll(v) : 2816LL; }();
+  static const int64_t min_k = tune_env("HV_GEMM_MT2_MINK", 2816);  // measured: 1280 loses 24 % on the level-0 FF2 (exposed single-buffered epilogue)
   if (K < min_k) return 1;  // 3x3 convs (K >= 2880) and the widest linears only: below that the exposed epilogue costs more than the L2 traffic saved
   const int64_t tiles2 = ((rows + 255) / 256) * ((N + bn - 1) / bn);
   return tiles2 >= sms ? 2 : 1;
@@ -130,7 +131,7 @@ int op_gemm(const __half* A, int64_t lda, const __half* A2, int64_t lda2, int64_
   // 128-row tiles: the output (and residual) slices move by TMA through per-warp shared-memory boxes
   CUtensorMap mo, mr;
   const CUtensorMap *pmo = nullptr, *pmr = nullptr;
-  static const int tma_io_env = [] { const char* v = getenv("HV_GEMM_TMA_IO"); return v ? atoi(v) : 1; }();
+  static const int tma_io_env = static_cast<int>(tune_env("HV_GEMM_TMA_IO", 1));
   if (m_sub == 1 && tma_io_env) {
     const int bc = gemm_io_box_cols(bn, geglu);
     if (!make_map_2d_io(&mo, out, M, e.n_valid, ldc, 32, bc)) { set_error("hv_op_gemm out map: %s", tma_last_error()); return HV_ERR_TMA; }
