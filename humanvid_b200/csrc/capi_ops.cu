@@ -46,6 +46,16 @@ int hv_pack_upconv2x2(const void* W, void* out, int64_t Cout, int64_t Cin, hv_st
   CK(launch_pack_upconv2x2(H(W), HM(out), (int)Cout, (int)Cin, device_sms(), ST(stream)), "hv_pack_upconv2x2");
 }
 
+int hv_op_conv3x3_small(const void* X, const void* Wp, const void* bias, void* out, int64_t ldo, int64_t NF, int64_t Hh, int64_t W, int64_t Cin,
+                        int64_t Cout, int32_t stride, int32_t act, hv_stream_t stream) {
+  if (!smallconv_supported((int)Cin, (int)Cout, stride)) { set_error("hv_op_conv3x3_small: (Cin, Cout, stride) = (%lld, %lld, %d) is not one of (16,16,1) (16,32,2) (32,32,1) (32,96,2)", (long long)Cin, (long long)Cout, stride); return HV_ERR_INVALID; }
+  CK(launch_smallconv(H(X), H(Wp), H(bias), HM(out), (int)NF, (int)Hh, (int)W, (int)Cin, (int)Cout, stride, (int)ldo, act, ST(stream)), "hv_op_conv3x3_small");
+}
+int hv_op_pose_conv_in(const void* X, const void* W, const void* bias, void* out, int64_t B, int64_t F, int64_t Hh, int64_t Wd, int32_t act, hv_stream_t stream) {
+  if (!device_sms()) return HV_ERR_CUDA;
+  CK(launch_pg_conv_in(H(X), H(W), H(bias), HM(out), (int)B, (int)F, (int)Hh, (int)Wd, act, device_sms(), ST(stream)), "hv_op_pose_conv_in");
+}
+
 int hv_op_conv3x3_direct(const void* X, const void* W, const void* bias, void* out, int64_t NF, int64_t Hh, int64_t Wd,
                          int64_t Cin, int64_t Cout, int32_t stride, int32_t act, const void* add, hv_stream_t stream) {
   if (!device_sms()) return HV_ERR_CUDA;

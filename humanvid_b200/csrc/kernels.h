@@ -42,6 +42,13 @@ cudaError_t launch_conv3x3_direct_padded(const __half* x, const __half* w, const
 cudaError_t launch_pack_upconv2x2(const __half* w, __half* out, int Cout, int Cin, int num_sms, cudaStream_t s);
 cudaError_t launch_pack_geglu(const __half* w, __half* out, int rows, int K, int num_sms, cudaStream_t s);
 cudaError_t launch_pack_heads(const __half* w, __half* out, int heads, int d, int dpad, int K, int num_sms, cudaStream_t s);
+// ---- small-channel convolutions of the PoseGuider front (smallconv.cu)
+bool smallconv_supported(int cin, int cout, int stride);
+cudaError_t launch_smallconv(const __half* x, const __half* wp, const __half* bias, __half* out, int NF, int H, int W, int cin, int cout, int stride,
+                             int ldo, int act, cudaStream_t s);
+cudaError_t launch_pg_conv_in(const __half* x, const __half* w, const __half* bias, __half* out, int B, int F, int H, int W, int act, int num_sms,
+                              cudaStream_t s);
+
 // ---- per-timestep glue of the denoising loop (step.cu)
 constexpr int kMaxWindows = 32;
 struct StepPreds {                       // window w's UNet prediction, (Bl, C, Fw, HW) fp16 each; cond unused without CFG

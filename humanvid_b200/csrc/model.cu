@@ -229,6 +229,8 @@ struct hv_model {
   ConvDirect pg_in;
   std::vector<Conv3> pg_convs;  // blocks.0..5, conv_out
   std::vector<int> pg_strides;
+  std::vector<bool> pg_small;   // layer runs on the small-channel mma.sync kernel at its true channel counts (smallconv.cu)
+  bool pg_fast_in = false;      // conv_in reads the (B,3,F,H,W) image directly and writes 16 channels (no layout pass, no padding)
   // ---- CameraPoseEncoder
   Conv3 cam_in;
   std::vector<CamResW> cam_res;
@@ -474,19 +476,45 @@ struct hv_model {
     for (size_t i = 0; i < readers.size(); ++i) readers[i]->reader_idx = static_cast<int>(i);
   }
 
+  // unpadded [cout][9 * cin] packing for the small-channel kernel
+  Conv3 conv3_small(const std::string& pfx, int cout, int cin) {
+    const Raw& r = get(pfx + ".weight");
+    if (r.shape.size() != 4 || r.shape[0] != cout || r.shape[1] != cin || r.shape[2] != 3 || r.shape[3] != 3)
+      fail(HV_ERR_INVALID, "weight '%s.weight' is not (%d,%d,3,3)", pfx.c_str(), cout, cin);
+    Conv3 c;
+    c.cin = c.cin_pad = cin;
+    c.cout = c.cout_pad = cout;
+    c.w.rows = cout;
+    c.w.cols = 9LL * cin;
+    c.w.p = dmalloc(c.w.rows * c.w.cols);
+    ck(launch_pack_conv3x3(r.p, c.w.p, cout, cin, cout, cin, sms, st), "pack small conv3x3");
+    c.bias = vec(pfx + ".bias", cout);
+    return c;
+  }
+
   void build_pose_guider() {
     const int* bc = cfg.pg_block_channels;
     pg_in = conv_direct("conv_in", bc[0], cfg.pg_cond_channels);
     pg_convs.clear();
     pg_strides.clear();
+    pg_small.clear();
+    // the 16 / 32-channel layers at (up to) full image resolution are HBM-bound: they run at their true channel counts on the small-channel
+    // kernel as long as the chain from conv_in is unbroken; from the first layer it does not cover, the tcgen05 implicit GEMM takes over
+    pg_fast_in = cfg.pg_cond_channels == 3 && bc[0] == 16 && smallconv_supported(bc[0], bc[0], 1);
+    bool chain = pg_fast_in;
     for (int i = 0; i < 3; ++i) {
-      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i), bc[i], bc[i], true, true));
-      pg_strides.push_back(1);
-      pg_convs.push_back(conv3("blocks." + std::to_string(2 * i + 1), bc[i + 1], bc[i], true, true));
-      pg_strides.push_back(2);
+      for (int k = 0; k < 2; ++k) {
+        const int cin = bc[i], cout = k == 0 ? bc[i] : bc[i + 1], stride = k == 0 ? 1 : 2;
+        const std::string name = "blocks." + std::to_string(2 * i + k);
+        chain = chain && smallconv_supported(cin, cout, stride);
+        pg_small.push_back(chain);
+        pg_convs.push_back(chain ? conv3_small(name, cout, cin) : conv3(name, cout, cin, true, true));
+        pg_strides.push_back(stride);
+      }
     }
     pg_convs.push_back(conv3("conv_out", cfg.pg_out_channels, bc[3]));
     pg_strides.push_back(1);
+    pg_small.push_back(false);
   }
 
   void build_camera() {
@@ -863,17 +891,44 @@ struct hv_model {
   void pose_guider_forward(const __half* cond, __half* outp, int B, int F, int H, int W) {
     const int NF = B * F;
     if ((H % 8) || (W % 8)) fail(HV_ERR_INVALID, "pose image %dx%d must be a multiple of 8", H, W);
-    Tens x0 = alloc_act(NF, H, W, cfg.pg_cond_channels);
-    Tens h = alloc_act(NF, H, W, pg_convs[0].cin_pad);
-    if (!ar.dry) {
-      launches += 3;
-      ck(launch_ncfhw_to_nhwc(cond, x0.p, B, cfg.pg_cond_channels, F, H, W, 0, st), "pose image layout");
-      ck(cudaMemsetAsync(h.p, 0, static_cast<size_t>(h.numel()) * 2, st), "memset");
-      ck(launch_conv3x3_direct_padded(x0.p, pg_in.w, pg_in.bias, h.p, NF, H, W, pg_in.cin, pg_in.cout, h.C, HV_ACT_SILU, sms, st), "pose conv_in");
+    Tens h;
+    if (pg_fast_in) {
+      // conv_in (3 -> 16) straight from the (B, 3, F, H, W) image: no layout pass, 16-channel output
+      h = alloc_act(NF, H, W, pg_in.cout);
+      if (!ar.dry) {
+        launches += 1;
+        Timed tm(this, CAT_CONV, 2.0 * h.rows() * pg_in.cout * 9.0 * pg_in.cin, "pg_conv_in", h.rows(), pg_in.cout, 9LL * pg_in.cin);
+        ck(launch_pg_conv_in(cond, pg_in.w, pg_in.bias, h.p, B, F, H, W, HV_ACT_SILU, sms, st), "pose conv_in");
+      }
+    } else {
+      Tens x0 = alloc_act(NF, H, W, cfg.pg_cond_channels);
+      h = alloc_act(NF, H, W, pg_convs[0].cin_pad);
+      if (!ar.dry) {
+        launches += 3;
+        ck(launch_ncfhw_to_nhwc(cond, x0.p, B, cfg.pg_cond_channels, F, H, W, 0, st), "pose image layout");
+        ck(cudaMemsetAsync(h.p, 0, static_cast<size_t>(h.numel()) * 2, st), "memset");
+        ck(launch_conv3x3_direct_padded(x0.p, pg_in.w, pg_in.bias, h.p, NF, H, W, pg_in.cin, pg_in.cout, h.C, HV_ACT_SILU, sms, st), "pose conv_in");
+      }
     }
     for (size_t i = 0; i < pg_convs.size(); ++i) {
       const bool last = i + 1 == pg_convs.size();
-      h = op_conv3(h, pg_convs[i], pg_strides[i], nullptr, 1, last ? HV_ACT_NONE : HV_ACT_SILU, nullptr);
+      const Conv3& c = pg_convs[i];
+      if (pg_small[i]) {
+        // the next layer either is a small-channel layer too (dense channels) or the first implicit-GEMM layer (its 64-multiple k-blocks)
+        const int ld = pg_small[i + 1] ? c.cout : pg_convs[i + 1].cin_pad;
+        const int Ho = pg_strides[i] == 1 ? h.H : h.H / 2, Wo = pg_strides[i] == 1 ? h.W : h.W / 2;
+        if (h.C != c.cin) fail(HV_ERR_INVALID, "pose guider small conv %zu: input has %d channels, expects %d", i, h.C, c.cin);
+        Tens out = alloc_act(NF, Ho, Wo, ld);
+        if (!ar.dry) {
+          if (ld > c.cout) { launches += 1; ck(cudaMemsetAsync(out.p, 0, static_cast<size_t>(out.numel()) * 2, st), "memset"); }
+          launches += 1;
+          Timed tm(this, CAT_CONV, 2.0 * out.rows() * c.cout * 9.0 * c.cin, pg_strides[i] == 1 ? "smallconv" : "smallconv_s2", out.rows(), c.cout, 9LL * c.cin);
+          ck(launch_smallconv(h.p, c.w.p, c.bias, out.p, NF, h.H, h.W, c.cin, c.cout, pg_strides[i], ld, HV_ACT_SILU, st), "pose small conv");
+        }
+        h = out;
+        continue;
+      }
+      h = op_conv3(h, c, pg_strides[i], nullptr, 1, last ? HV_ACT_NONE : HV_ACT_SILU, nullptr);
       // the next conv expects cin_pad channels: cout_pad of this conv equals it by construction (both round to 64)
       if (!last && h.C != pg_convs[i + 1].cin_pad) fail(HV_ERR_INVALID, "pose guider channel padding mismatch at conv %zu", i);
     }

@@ -67,6 +67,17 @@ int hv_op_gemm_batched_b(const void* A, int64_t lda, const void* X, int64_t ldx,
                          int64_t rows, int64_t out_stride, int64_t K, const void* rowbias /* fp16 [M] added to row m, or NULL */,
                          hv_stream_t stream);
 
+/* The small-channel 3x3 convolutions of the PoseGuider front (src/models/pose_guider.py:25-49) at their true channel counts (HBM-bound
+ * layers at up to full image resolution; mma.sync implicit GEMM over a shared-memory halo tile): (Cin, Cout, stride) in
+ * {(16,16,1), (16,32,2), (32,32,1), (32,96,2)}, padding 1, + bias, act.  X (NF, H, W, Cin) channels-last; Wp = hv_pack_conv3x3 with
+ * Cin_pad = Cin, Cout_pad = Cout ([Cout][9 * Cin]); out (NF, Ho, Wo, ldo >= Cout), columns >= Cout are left untouched.
+ * hv_op_pose_conv_in: the PoseGuider's conv_in (3 -> 16) read straight from the (B, 3, F, H, W) image, W in the reference layout (16,3,3,3),
+ * out channels-last (B*F, H, W, 16). */
+int hv_op_conv3x3_small(const void* X, const void* Wp, const void* bias, void* out, int64_t ldo, int64_t NF, int64_t H, int64_t W, int64_t Cin,
+                        int64_t Cout, int32_t stride, int32_t act, hv_stream_t stream);
+int hv_op_pose_conv_in(const void* X, const void* W, const void* bias, void* out, int64_t B, int64_t F, int64_t H, int64_t W_, int32_t act,
+                       hv_stream_t stream);
+
 /* Upsample3D (src/models/resnet.py:29-88): nearest 2x upsample followed by the 3x3 convolution, WITHOUT materialising the upsampled
  * tensor: every output parity (2y+py, 2x+px) is a 2x2 convolution of the source whose weights are sums of the 3x3 taps that land on
  * the same source pixel (4/9 of the multiply-adds; the summed weights are rounded to fp16 once, at packing).

@@ -131,6 +131,38 @@ def test_upconv2x2_is_upsample_then_conv(NF, H, W, Cin, Cout):
     assert rel(out, ref) < 1e-3, rel(out, ref)
 
 
+@pytest.mark.parametrize("NF,H,W,Cin,Cout,stride", [(2, 64, 96, 16, 16, 1), (3, 40, 72, 16, 32, 2), (2, 20, 36, 32, 32, 1), (2, 36, 20, 32, 96, 2), (1, 768, 576, 16, 16, 1),
+                                                      (1, 192, 144, 32, 96, 2), (2, 13, 7, 16, 16, 1)])
+def test_conv3x3_small_channels_mma(NF, H, W, Cin, Cout, stride):
+    """PoseGuider front layers (pose_guider.py:25-49) at true channel counts: + bias, SiLU, optional padded output row stride."""
+    if stride == 2 and (H % 2 or W % 2):
+        pytest.skip("stride 2 needs even sizes")
+    x = dev(NF, H, W, Cin, seed=33)
+    w = dev(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=34)
+    bias = dev(Cout, seed=35)
+    wp = torch.empty(Cout, 9 * Cin, device="cuda", dtype=torch.half)
+    check(lib().hv_pack_conv3x3(ptr(w), ptr(wp), i64(Cout), i64(Cin), i64(Cout), i64(Cin), stream()))
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    ldo = Cout if Cout != 96 else 128          # blocks.3 writes into the 128-channel k-block layout of the next implicit-GEMM conv
+    out = torch.full((NF, Ho, Wo, ldo), 7.0, device="cuda", dtype=torch.half)
+    check(lib().hv_op_conv3x3_small(ptr(x), ptr(wp), ptr(bias), ptr(out), i64(ldo), i64(NF), i64(H), i64(W), i64(Cin), i64(Cout), i32(stride), i32(2), stream()))
+    ref = F.silu(conv_ref(x, w, bias, stride))
+    torch.cuda.synchronize()
+    assert rel(out[..., :Cout], ref) < 1e-3, rel(out[..., :Cout], ref)
+    assert bool((out[..., Cout:] == 7.0).all())     # pad columns untouched
+
+
+def test_pose_conv_in_from_planar_image():
+    B, Fr, H, W = 1, 3, 40, 56
+    img = torch.rand(B, 3, Fr, H, W, device="cuda").half()
+    w, b = dev(16, 3, 3, 3, scale=0.2, seed=36), dev(16, seed=37)
+    out = torch.zeros(B * Fr, H, W, 16, device="cuda", dtype=torch.half)
+    check(lib().hv_op_pose_conv_in(ptr(img), ptr(w), ptr(b), ptr(out), i64(B), i64(Fr), i64(H), i64(W), i32(2), stream()))
+    ref = F.silu(F.conv2d(img[0].permute(1, 0, 2, 3).float(), w.float(), b.float(), padding=1)).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-3
+
+
 def test_conv3x3_direct_small_channels():
     NF, H, W, Cin, Cout = 2, 32, 24, 3, 16
     x, w, b = dev(NF, H, W, Cin, seed=30), dev(Cout, Cin, 3, 3, scale=0.2, seed=31), dev(Cout, seed=32)
