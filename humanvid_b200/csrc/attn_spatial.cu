@@ -668,11 +668,31 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_wait(&bar_s[g], j & 1);
       tc_fence_after();
       tick(0);
-      // pass 1: my half's row max.  The second 32-key chunk stays in registers for pass 2; the first is re-read from
-      // TMEM, the load being issued here so that its latency hides behind the row-max exchange.
+      // pass 1: the row max over all 128 keys of the tile, computed by BOTH threads of the row -- the other half's 64 scores are read from
+      // TMEM for the max only.  (Exchanging two half-row maxima through shared memory cost a 256-thread named barrier per key tile,
+      // ~440 clocks of the ~2600 a tile takes; fmax is exact, so the two threads still agree bit for bit on `grow`.)
       float mx0 = -INFINITY, mx1 = -INFINITY;
       uint32_t raw0[32], raw1[32];
-      tmem_ld32(my_s, raw0);
+      {
+        const int kv_other = kv_valid + (2 * hf - 1) * 64;     // valid keys in the other half of the tile
+        tmem_ld32(tmem_s + lane_off + (1 - hf) * 64, raw0);
+        tmem_ld32(tmem_s + lane_off + (1 - hf) * 64 + 32, raw1);
+        tmem_ld_wait();
+        if (64 <= kv_other) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(raw0[i]), __uint_as_float(raw1[i])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(raw0[i + 1]), __uint_as_float(raw1[i + 1])));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < kv_other) mx0 = fmaxf(mx0, __uint_as_float(raw0[i]));
+            if (32 + i < kv_other) mx1 = fmaxf(mx1, __uint_as_float(raw1[i]));
+          }
+        }
+      }
+      tmem_ld32(my_s, raw0);          // my half: kept in registers for pass 2
       tmem_ld32(my_s + 32, raw1);
       tmem_ld_wait();
       if (64 <= kv_valid) {
@@ -689,16 +709,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
       tick(1);
-      tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
-      float* sm = gmax + (j & 1) * 256;
-      sts_f32(sm + hf * 128 + r, fmaxf(mx0, mx1) * sc);
-      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 2, 256;" ::: "memory");
-      const float rowmax = fmaxf(lds_f32(sm + r), lds_f32(sm + 128 + r));
+      const float rowmax = fmaxf(mx0, mx1) * sc;
       const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
       const float m_new = grow ? rowmax : m_used;
       tick(2);
-      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar_sfree[g]);   // all my reads of S are done: the MMA warp may overwrite it with the next tile's scores
       if (j > 0) {

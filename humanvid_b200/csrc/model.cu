@@ -555,7 +555,7 @@ struct hv_model {
     Tens out = alloc_act(x.NF, x.H, x.W, x.C + C2);
     float* stats = static_cast<float*>(ar.alloc(sizeof(float) * groupnorm_scratch_floats(x.C + C2, x.NF, x.H * x.W, cfg.norm_groups, sms)));
     if (ar.dry) return out;
-    launches += 3;
+    launches += 2;
     Timed tm(this, CAT_NORM, 0, "groupnorm", x.rows(), x.C + C2, 0);
     ck(launch_groupnorm(x.p, x.C, x2 ? x2->p : nullptr, C2, n.g, n.b, out.p, x.NF, x.H * x.W, cfg.norm_groups, n.eps, silu ? 1 : 0, stats, sms, st),
        "groupnorm");
@@ -736,11 +736,22 @@ struct hv_model {
     // ---- attn2 with a single key: softmax == 1 -> out = to_out(to_v(ehs_b)) for every token of batch item b
     __half* v2 = op_small_linear(ehs, w.v2, B, HV_ACT_NONE);
     __half* ca = op_small_linear(v2, w.out2, B, HV_ACT_NONE);
-    Tens t2;
-    Tens n3 = op_ln(t1, w.ln3, ca, static_cast<int64_t>(F) * L, &t2, nullptr, 1);
+    // LayerNorm-3 normalises t2 = t1 + ca[b] without writing t2: the same per-batch vector is added again, in fp32, in FF2's epilogue
+    // (t3 = ff2(.) + bias + ca[b] + t1), which saves one full-tensor write per block and one rounding of the residual stream
+    Tens n3 = op_ln(t1, w.ln3, ca, static_cast<int64_t>(F) * L, nullptr, nullptr, 1);
     // ---- feed-forward
     Tens ffh = op_linear(n3, w.ff1, nullptr, HV_ACT_NONE, true);
-    Tens t3 = op_linear(ffh, w.ff2, &t2);
+    Tens t3 = alloc_act(x.NF, x.H, x.W, C);
+    {
+      hv_epilogue ep{};
+      ep.bias = w.ff2.bias;
+      ep.rowvec = ca;
+      ep.rowvec_ld = C;
+      ep.rows_per_group = static_cast<int32_t>(static_cast<int64_t>(F) * L);
+      ep.residual = t1.p;
+      ep.ldr = C;
+      gemm(ffh.p, ffh.C, nullptr, 0, 0, w.ff2.w, t3.p, C, tokens, &ep);
+    }
     // ---- proj_out + residual
     hv_epilogue ep{};
     ep.bias = w.proj_out.bias;

@@ -32,7 +32,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 
 // ---------------------------------------------------------------- GroupNorm statistics (deterministic: no atomics)
 // grid (slabs, NF); thread = (row lane, 8-channel vector).  Each block writes its per-group {sum, sumsq} to
-// partial[n][slab][g]; gn_finalize_kernel adds the slabs in a fixed order -> {mean, rstd}.
+// partial[n][slab][g]; gn_apply_kernel adds the slabs in a fixed order -> {mean, rstd}.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int groups,
                                 int rows_per_block, float* __restrict__ partial) {
   extern __shared__ float sred[];  // [blockDim.x][4][2]
@@ -97,29 +97,13 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, const __h
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int total, int groups, int slabs, float inv_cnt,
-                                   float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * groups + g
-  if (i >= total) return;
-  const int n = i / groups, g = i % groups;
-  float ss = 0.f, qq = 0.f;
-  for (int sl = 0; sl < slabs; ++sl) {
-    const float* p = partial + ((static_cast<long long>(n) * slabs + sl) * groups + g) * 2;
-    ss += p[0];
-    qq += p[1];
-  }
-  const float mean = ss * inv_cnt;
-  const float var = fmaxf(qq * inv_cnt - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
-}
-
 // grid (slabs, NF), thread = (row lane, 8-channel vector) like the statistics kernel: the thread's channels are fixed, so
 // gamma/beta/mean/rstd fold into one per-channel scale and shift kept in registers, and the row loop has no integer
 // division and one FFMA + SiLU per element.
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
-                                int HW, int groups, int rows_per_block, int silu, const float* __restrict__ stats) {
+                                int HW, int groups, int rows_per_block, int silu, const float* __restrict__ partial, int slabs, float inv_cnt,
+                                float eps) {
   const int C = C1 + C2, vecs = C / 8, cpg = C / groups;
   const int n = blockIdx.y;
   const int rl = threadIdx.x / vecs, v = threadIdx.x % vecs, rpi = blockDim.x / vecs;
@@ -131,8 +115,16 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
     unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c0)), bt);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      // finalize folded in: add this (frame, group)'s per-slab partial sums in slab order (fixed order -> deterministic) -> mean, rstd
       const int g = (c0 + 2 * k) / cpg;
-      const float2 st = __ldg(reinterpret_cast<const float2*>(stats + (static_cast<long long>(n) * groups + g) * 2));
+      float ss = 0.f, qq = 0.f;
+      for (int sl = 0; sl < slabs; ++sl) {
+        const float2 pp = __ldg(reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * slabs + sl) * groups + g) * 2));
+        ss += pp.x;
+        qq += pp.y;
+      }
+      const float mean = ss * inv_cnt;
+      const float2 st = make_float2(mean, rsqrtf(fmaxf(qq * inv_cnt - mean * mean, 0.f) + eps));
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         sc[2 * k + j] = st.y * gm[2 * k + j];
@@ -289,9 +281,9 @@ cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2,
   if (threads < groups) return cudaErrorInvalidValue;
   float* partial = stats + static_cast<size_t>(2) * NF * groups;
   gn_stats_kernel<<<dim3(slabs, NF), threads, threads * 8 * sizeof(float), stream>>>(x1, C1, x2, C2, HW, groups, rows_per_block, partial);
-  const int total_g = NF * groups;
-  gn_finalize_kernel<<<(total_g + 127) / 128, 128, 0, stream>>>(partial, stats, total_g, groups, slabs, 1.f / (static_cast<float>(HW) * (C / groups)), eps);
-  gn_apply_kernel<<<dim3(slabs, NF), threads, 0, stream>>>(x1, C1, x2, C2, gamma, beta, out, HW, groups, rows_per_block, silu, stats);
+  // (the {mean, rstd} finalize is folded into the apply kernel: one launch less per GroupNorm, 83 per forward)
+  gn_apply_kernel<<<dim3(slabs, NF), threads, 0, stream>>>(x1, C1, x2, C2, gamma, beta, out, HW, groups, rows_per_block, silu, partial, slabs,
+                                                           1.f / (static_cast<float>(HW) * (C / groups)), eps);
   return cudaGetLastError();
 }
 

@@ -143,46 +143,63 @@ smallconv_mma_kernel(const __half* __restrict__ x, const __half* __restrict__ wp
 }
 
 // conv_in of the PoseGuider: (B, 3, F, H, W) fp16 planes -> channels-last (B*F, H, W, 16), 3x3, padding 1, + bias, SiLU.
+// One thread = two horizontally adjacent pixels x 16 channels: every weight fetched from shared memory (a broadcast LDS) feeds two FMAs
+// -- with one pixel per thread the kernel was bound by the 432 LDS per pixel, not by its 432 FMAs or its 64 + 340 MB of traffic.
 __global__ void __launch_bounds__(256) pg_conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                                                          __half* __restrict__ out, int B, int F, int H, int W, int act) {
   __shared__ float ws[16 * 27 + 16];
   for (int i = threadIdx.x; i < 16 * 27; i += blockDim.x) ws[i] = __half2float(w[i]);   // (16, 3, 3, 3) as is: [co][ci][ky][kx]
   for (int i = threadIdx.x; i < 16; i += blockDim.x) ws[16 * 27 + i] = bias ? __half2float(bias[i]) : 0.f;
   __syncthreads();
-  const long long HW = static_cast<long long>(H) * W, total = static_cast<long long>(B) * F * HW;
+  const int W2 = (W + 1) / 2;
+  const long long HW = static_cast<long long>(H) * W, total = static_cast<long long>(B) * F * H * W2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xx = static_cast<int>(i % W);
-    long long t = i / W;
+    const int xx = static_cast<int>(i % W2) * 2;
+    long long t = i / W2;
     const int yy = static_cast<int>(t % H);
     const long long nf = t / H;
     const int b = static_cast<int>(nf / F), f = static_cast<int>(nf % F);
-    float in[27];
+    float in[3][3][4];   // [ci][ky][columns xx-1 .. xx+2]
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
       const __half* plane = x + ((static_cast<long long>(b) * 3 + ci) * F + f) * HW;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int gy = yy + ky - 1;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int gy = yy + ky - 1, gx = xx + kx - 1;
-          in[ci * 9 + ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __half2float(__ldg(plane + static_cast<long long>(gy) * W + gx)) : 0.f;
+        for (int c = 0; c < 4; ++c) {
+          const int gx = xx + c - 1;
+          in[ci][ky][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __half2float(__ldg(plane + static_cast<long long>(gy) * W + gx)) : 0.f;
         }
+      }
     }
-    uint32_t o[8];
+    uint32_t o0[8], o1[8];
 #pragma unroll
     for (int cp = 0; cp < 8; ++cp) {
-      float v0 = ws[16 * 27 + 2 * cp], v1 = ws[16 * 27 + 2 * cp + 1];
+      float a0 = ws[16 * 27 + 2 * cp], a1 = ws[16 * 27 + 2 * cp + 1], b0 = a0, b1 = a1;   // pixel xx: a*, pixel xx + 1: b*
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        v0 = fmaf(in[k], ws[(2 * cp) * 27 + k], v0);
-        v1 = fmaf(in[k], ws[(2 * cp + 1) * 27 + k], v1);
-      }
-      if (act == 2) { v0 = silu_f(v0); v1 = silu_f(v1); }
-      o[cp] = pack_h2(v0, v1);
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float w0 = ws[(2 * cp) * 27 + ci * 9 + ky * 3 + kx], w1 = ws[(2 * cp + 1) * 27 + ci * 9 + ky * 3 + kx];
+            a0 = fmaf(in[ci][ky][kx], w0, a0);
+            a1 = fmaf(in[ci][ky][kx], w1, a1);
+            b0 = fmaf(in[ci][ky][kx + 1], w0, b0);
+            b1 = fmaf(in[ci][ky][kx + 1], w1, b1);
+          }
+      if (act == 2) { a0 = silu_f(a0); a1 = silu_f(a1); b0 = silu_f(b0); b1 = silu_f(b1); }
+      o0[cp] = pack_h2(a0, a1);
+      o1[cp] = pack_h2(b0, b1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
-    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    uint4* dst = reinterpret_cast<uint4*>(out + ((nf * H + yy) * W + xx) * 16);
+    dst[0] = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+    dst[1] = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+    if (xx + 1 < W) {
+      dst[2] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      dst[3] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+    }
   }
 }
 
@@ -222,7 +239,7 @@ cudaError_t launch_smallconv(const __half* x, const __half* wp, const __half* bi
 
 cudaError_t launch_pg_conv_in(const __half* x, const __half* w, const __half* bias, __half* out, int B, int F, int H, int W, int act, int num_sms,
                               cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * F * H * W;
+  const long long total = static_cast<long long>(B) * F * H * ((W + 1) / 2);
   long long blocks = (total + 255) / 256;
   if (blocks > static_cast<long long>(num_sms) * 32) blocks = static_cast<long long>(num_sms) * 32;
   pg_conv_in_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, out, B, F, H, W, act);

@@ -1,6 +1,9 @@
 """Timing + accuracy of hv_op_attention at one shape: python scripts/attn_bench.py NF L heads d   (env HV_ATTN_POLY / HV_ATTN_WARPS)"""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import humanvid_b200._native as _N
+if os.environ.get("HV_LIB"):   # A/B against another build of the library
+    _N.LIB_PATH = os.environ["HV_LIB"]
 from humanvid_b200._native import check, i32, i64, lib, ptr, stream
 
 NF, L, heads, d = [int(v) for v in sys.argv[1:5]]

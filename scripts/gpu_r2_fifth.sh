@@ -7,3 +7,4 @@ timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k re
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 18 -o gpurun_out/prof_gemm_v2 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-extras > gpurun_out/ncu_gemm2.log 2>&1; echo "== ncu gemm rc=$?"
 ls -la gpurun_out/*.ncu-rep; du -sh gpurun_out
 HV_TRACE=gpurun_out/trace_c2_e.csv timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c2_final.log 2>&1; echo "== bench c2 rc=$?"; tail -n 1 gpurun_out/bench_c2_final.log | cut -c1-300
+timeout -s KILL 400 python scripts/graph_gain.py 2>&1 | tail -4
