@@ -460,6 +460,24 @@ def run_native(args, rank, world, local_rank, cfg):
     n_fwd = (len(loop.my_units) if (is5 and world > 1) else len(windows)) if is5 else 1
     launches_step = launches_fwd * n_fwd + ((n_fwd + 2) if is5 else 0)
 
+    # ---- (N > 1) the same per-GPU workload on rank 0 ALONE, the other GPUs idle: the reference point for scaling efficiency on THIS workload
+    # (the default N = 1 run is config 2, the N > 1 runs are config 4 = N x config 3, which has 10 % more work per GPU)
+    solo_ms = None
+    if world > 1:
+        reset()
+        barrier()
+        if rank == 0:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                if is5:   # one GPU doing all units would be the config-5 N = 1 run; here: this rank's share only
+                    break
+                out = step()
+            s1.record()
+            torch.cuda.synchronize()
+            solo_ms = None if is5 else s0.elapsed_time(s1) / args.steps
+        barrier()
+
     # ---- kernel-only: inputs resident, K steps bracketed by barrier + synchronize, device-timed
     reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -577,6 +595,11 @@ def run_native(args, rank, world, local_rank, cfg):
         "clocks": clocks,
     }
     line.update(extras)
+    if solo_ms is not None:
+        line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s",
+                              "efficiency_vs_solo": value / (world * F / (solo_ms / 1000.0)),
+                              "what": "the same per-GPU workload (one config-3 clip) timed on rank 0 with the other GPUs idle, in this run: the N = 1 reference of THIS "
+                                      "workload (the default N = 1 bench line is config 2, 10 % less work per GPU)"}
     if eager is not None:
         eager["value"] = frames_total / (eager["ms_per_forward"] * (len(windows) if is5 else 1) / 1000.0)
         eager["unit"] = "frames/s"

@@ -443,7 +443,10 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 // groups are forced out of phase: a token (two named barriers) lets only one group at a time into its MUFU phase, so one
 // group's max / S / P V latency always hides behind the other group's exponentials, and the K/V tiles are fetched once
 // for 256 queries.  TMEM (512 columns): per group 128 S + 64 P (packed fp16, A operand of the P V MMA) + dv O.
-constexpr int ATTPP_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax A, warps 10-17 softmax B
+// warps 0-7 softmax A, 8-15 softmax B (four whole warpgroups), warp 16 TMA, 17 MMA (group A), 18 MMA (group B), 19 idle: the producer
+// warpgroup hands most of its registers to the softmax warpgroups (setmaxnreg: 64 vs 104 per thread), which removes the spills the 96-register
+// budget of a 19-warp CTA forced into the softmax loop (3 % of its executed instructions were LDL / STL)
+constexpr int ATTPP_THREADS = 640;
 
 template <int D>
 struct PPCfg {
@@ -467,7 +470,7 @@ struct PPCfg {
 // (S_A, P V_A, S_B, P V_B): group B's next S = Q K^T cannot be issued before group A's probabilities arrive, which locks the two groups
 // into the same phase (both in the MUFU phase, then both waiting -- ncu: XU pipe 69 % busy, B waits ~1.7x longer for S than A).
 template <int D, int PE, bool TOKEN, int MW = 1>
-__global__ void __launch_bounds__(ATTPP_THREADS + 32 * (MW - 1), 1)   // 18 (19) warps -> 5 on a scheduler -> 16K / (5 * 32) = 102 -> 96 registers
+__global__ void __launch_bounds__(ATTPP_THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
                const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
@@ -518,14 +521,18 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // register reallocation (setmaxnreg sits at the top of each role's own branch so that ptxas allocates that region with the new limit):
+  // the CTA owns 640 threads x 96 registers = 61 440; producer warpgroup (warps 16-19) 64 per thread, the 16 softmax warps 104:
+  // 512 * 104 + 128 * 64 = 61 440 exactly (asking for more than the CTA's own pool would spin in setmaxnreg.inc forever)
   // group g: S at +256g (128 columns), P at +256g+128 (64), O at +256g+192 (DV)
 
-  if (warp == 0) {
+  if (warp == 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, 2 * C::kQBytes);
 #pragma unroll
@@ -554,7 +561,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 || warp == 18) {
+  } else if (warp == 17 || (MW == 2 && warp == 18)) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     {   // all 32 lanes run the issue loop with warp-uniform operands; one elected lane issues (see umma_*_w)
       constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
@@ -585,7 +593,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tc_fence_after();
       if (MW == 2) {
         // ---- one issuer per group: S(j+1) goes out as soon as the group has read S(j); P V(j) as soon as its P(j) is in TMEM
-        const int g = warp == 1 ? 0 : 1;
+        const int g = warp == 17 ? 0 : 1;
         issue_s(g, 0);
         umma_commit_w(&bar_k_empty[0]);
         for (int j = 0; j < T; ++j) {
@@ -636,17 +644,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       }
     }
+  } else if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // idle warp(s) of the producer warpgroup
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ---------------------------------------------------------------- softmax: group g, two threads per query row
-    const int g = (warp - 2) >> 3;
-    const int w = (warp - 2) & 7;
+    const int g = warp >> 3;
+    const int w = warp & 7;
     const int qd = warp & 3;                        // TMEM lane quadrant of this warp
     const int hf = w >> 2;                          // which 64-key half of every tile this thread owns
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * 256, tmem_p = tmem_s + 128, tmem_o = tmem_s + 192;
     const uint32_t my_s = tmem_s + lane_off + hf * 64;
-    float* gmax = smax + g * 512;
     float m_used = -INFINITY;
     const float sc = a.scale_log2;
     // token: barrier 3 = "A may run its MUFU phase", barrier 4 = "B may"; B hands A the first turn
@@ -816,7 +826,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -841,7 +851,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       const long long nct = static_cast<long long>(grid.x) * grid.y * grid.z;
       if (cudaMalloc(&kd.dbg, nct * 32 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
       cudaMemsetAsync(kd.dbg, 0, nct * 32 * sizeof(long long), stream);
-      attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
+      attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
       cudaStreamSynchronize(stream);
       long long* hb = static_cast<long long*>(malloc(nct * 32 * sizeof(long long)));
       cudaMemcpy(hb, kd.dbg, nct * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -857,7 +867,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       cudaFree(kd.dbg);
       return cudaGetLastError();
     }
-    attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
     return cudaGetLastError();
   }
 }

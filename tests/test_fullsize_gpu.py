@@ -9,6 +9,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from conftest import report
+
 if torch.cuda.is_available():
     import humanvid_b200 as hv
     from oracle import hv_oracle as O
@@ -52,10 +54,13 @@ def test_config2_parity_full_size(full):
         ora.half()
     torch.cuda.synchronize()
     e_ref, e_nat, e_pair = rel(y16, y32), rel(yn, y32), rel(yn, y16)
-    print(f"config2 full size: fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}")
+    report(f"config2 full size (2,4,24,96,72): fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}")
     assert torch.isfinite(yn).all()
-    assert e_nat <= 1.5 * e_ref + 5e-4
-    assert e_pair <= 5e-3
+    # north_star: <= 1e-3 per tensor.  Per block on identical inputs it is 3e-4 (tests/test_ladder_gpu.py, profiles/r02_error_ladder_config2.txt);
+    # accumulated over the ~65 sequential fp16 tensors of a forward the storage roundings alone reach 1.4e-3 (the reference's own fp16 path:
+    # 1.7e-3), so the network-level bar is "closer to fp32 than the reference's deployment, and below 1.6e-3" (measured 1.40e-3 / 1.70e-3 / 1.98e-3)
+    assert e_nat <= e_ref and e_nat <= 1.6e-3
+    assert e_pair <= 2.5e-3
     # per-frame breakdown: no single frame may be an outlier
     per_frame = [(rel(yn[:, :, f], y32[:, :, f])) for f in range(F)]
     assert max(per_frame) <= 3 * (sum(per_frame) / F)
@@ -90,7 +95,7 @@ def test_config3_banks_full_size(full):
         O.set_reference_banks(ora, None)
         ctl.clear()
     torch.cuda.synchronize()
-    print(f"config3 full size: native vs fp16-eager oracle {rel(yn, y16):.2e}")
-    assert rel(yn, y16) <= 5e-3
+    report(f"config3 full size (16 banks): native vs fp16-eager oracle {rel(yn, y16):.2e}")
+    assert rel(yn, y16) <= 2.5e-3
     assert torch.equal(yn[:1], plain[:1])          # unconditional half never sees the bank
     assert rel(yn[1:], plain[1:]) > 1e-2           # conditional half does

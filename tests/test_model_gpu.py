@@ -2,10 +2,11 @@
 against the oracle on identical weights and inputs, the committed golden vectors (generated from the reference's own
 modules), and size-independent properties at the BASELINE config-2 shape.
 
-Tolerances.  north_star: <= 1e-3 relative (fp16) per tensor vs the reference PyTorch path.  The reference path in fp16
-is itself ~1e-3 away from exact arithmetic after ~100 layers, so two bars are checked:
-  * err(native, fp32 oracle) <= 1.5 * err(fp16-eager oracle, fp32 oracle) + 5e-4   (native is no worse than the reference's own rounding)
-  * err(native, fp16-eager oracle) <= 4e-3 on the full stack, per-op/per-block tests use 1e-3 (tests/test_ops_gpu.py)
+Tolerances.  north_star: <= 1e-3 relative (fp16) per tensor vs the reference PyTorch path.  Per operator (tests/test_ops_gpu.py) and
+per block on identical inputs (tests/test_ladder_gpu.py) that is what is asserted.  Through a whole network the fp16 storage roundings
+of ~65 sequential tensors accumulate to ~1.5e-3 in ANY fp16 implementation (the reference's own fp16-eager path: 1.7e-3), so there:
+  * err(native, fp32 oracle) <= err(fp16-eager oracle, fp32 oracle) + 1e-4   (native is no further from exact than the reference's deployment)
+  * err(native, fp16-eager oracle) <= 2.5e-3
 """
 import os
 
@@ -15,6 +16,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+from conftest import report
 
 if torch.cuda.is_available():
     import humanvid_b200 as hv
@@ -73,10 +76,10 @@ def test_unet_narrow_parity(narrow):
     x, ehs, pose = unet_inputs(2, 5, 16, 16, 64, 64)
     y32, y16, yn = run3(ora, nat, x, 721, ehs, pose)
     e_ref, e_nat, e_pair = rel(y16, y32), rel(yn, y32), rel(yn, y16)
-    print(f"narrow: fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}")
+    report(f"narrow: fp16-eager vs fp32 {e_ref:.2e}; native vs fp32 {e_nat:.2e}; native vs fp16-eager {e_pair:.2e}")
     assert torch.isfinite(yn).all()
-    assert e_nat <= 1.5 * e_ref + 5e-4
-    assert e_pair <= 4e-3
+    assert e_nat <= e_ref + 1e-4
+    assert e_pair <= 2.5e-3
 
 
 def test_unet_narrow_reference_banks_and_cfg(narrow):
@@ -96,7 +99,8 @@ def test_unet_narrow_reference_banks_and_cfg(narrow):
         yn = nat(x, 500, ehs, pose_cond_fea=pose, return_dict=False)[0].clone()
     O.set_reference_banks(ora, None)
     torch.cuda.synchronize()
-    assert rel(yn, y32) < 4e-3
+    report(f"narrow + banks + CFG: native vs fp32 {rel(yn, y32):.2e}")
+    assert rel(yn, y32) < 2.5e-3
     # CFG semantics: the uncond half never sees the bank -> bitwise equal to the plain forward; the cond half changes
     assert torch.equal(yn[:1], y_plain[:1])
     assert rel(yn[1:], y_plain[1:]) > 1e-2
@@ -110,7 +114,7 @@ def test_unet_narrow_reference_banks_and_cfg(narrow):
         ynb = nat(x, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
     O.set_reference_banks(ora, None)
     ctl2.clear()
-    assert rel(ynb, y32b) < 4e-3
+    assert rel(ynb, y32b) < 2.5e-3
     with torch.no_grad():
         y_again = nat(x, 500, ehs, pose_cond_fea=pose, return_dict=False)[0]
     assert torch.equal(y_again, y_plain)  # clear() restores plain self-attention, and the forward is deterministic
@@ -120,7 +124,8 @@ def test_unet_image_variant_no_motion_module():
     ora, nat = make_unet((64, 128, 256, 256), 64, motion=False)
     x, ehs, pose = unet_inputs(2, 1, 32, 32, 64, 64, seed=9)
     y32, y16, yn = run3(ora, nat, x, 999, ehs, pose)
-    assert rel(yn, y32) <= 1.5 * rel(y16, y32) + 5e-4
+    report(f"image variant (no motion module, F=1): native vs fp32 {rel(yn, y32):.2e}; fp16-eager vs fp32 {rel(y16, y32):.2e}")
+    assert rel(yn, y32) <= rel(y16, y32) + 1e-4
 
 
 def test_unet_full_width_against_reference_golden():
@@ -132,8 +137,8 @@ def test_unet_full_width_against_reference_golden():
         y16 = ora.half()(x, torch.tensor(g["t"], device="cuda"), ehs, pose_cond_fea=pose)[0]
     gold = g["y"].cuda()  # fp32 output of the reference's own modules (fp32 weights, fp32 inputs)
     e_nat, e_ref = rel(yn, gold), rel(y16, gold)
-    print(f"full-width tiny: native vs reference golden {e_nat:.2e}; fp16-eager vs golden {e_ref:.2e}")
-    assert e_nat <= 1.5 * e_ref + 1e-3
+    report(f"full-width tiny: native vs reference golden {e_nat:.2e}; fp16-eager vs golden {e_ref:.2e}")
+    assert e_nat <= e_ref + 2e-4
     del ora, nat
     torch.cuda.empty_cache()
 
@@ -160,8 +165,8 @@ def test_reference_writer_unet2d_golden_banks_and_chain():
     assert hid.shape == (2, 64, 16, 16) and [tuple(b.shape) for b in banks] == [tuple(b.shape) for b in g["banks"]]
     e_hid, e_ref = rel(hid, g["hidden"].cuda()), rel(hid16, g["hidden"].cuda())
     e_banks = [rel(b, gb.cuda()) for b, gb in zip(banks, g["banks"])]
-    print(f"writer UNet2D: hidden native vs reference golden {e_hid:.2e} (fp16-eager {e_ref:.2e}); banks max {max(e_banks):.2e}")
-    assert e_hid <= 1.5 * e_ref + 5e-4
+    report(f"writer UNet2D: hidden native vs reference golden {e_hid:.2e} (fp16-eager {e_ref:.2e}); banks max {max(e_banks):.2e}")
+    assert e_hid <= e_ref + 2e-4
     assert max(e_banks) <= 2e-3
     # writer -> reader on the native denoising UNet; reference chain value y3
     ora3, nat3 = make_unet((64, 128, 256, 256), 64, seed=g["seed3"])
@@ -173,8 +178,8 @@ def test_reference_writer_unet2d_golden_banks_and_chain():
         O.set_reference_banks(ora3, [gb.cuda().half() for gb in g["banks"]], cfg=True)
         y16 = ora3.half()(x3, torch.tensor(g["t3"], device="cuda"), ehs)[0]
     e_nat, e_16 = rel(y, g["y3"].cuda()), rel(y16, g["y3"].cuda())
-    print(f"writer -> reader chain: native vs reference golden {e_nat:.2e} (fp16-eager {e_16:.2e})")
-    assert e_nat <= 1.5 * e_16 + 5e-4
+    report(f"writer -> reader chain: native vs reference golden {e_nat:.2e} (fp16-eager {e_16:.2e})")
+    assert e_nat <= e_16 + 2e-4
     reader.clear(); writer.clear()
     # without write mode the forward is unchanged and leaves no banks
     nat._ref_write = False
@@ -197,8 +202,8 @@ def test_reference_writer_unet2d_full_width_config2_shape():
     banks, banks32 = [b.bank[0] for b, _ in nat.writer_blocks()], O.written_banks(ora)
     assert [tuple(b.shape[1:]) for b in banks] == [(432, 1280)] * 5 + [(108, 1280)] + [(1728, 640)] * 5 + [(6912, 320)] * 5
     errs = [rel(a, b) for a, b in zip(banks, banks32)]
-    print(f"writer UNet2D full width 96x72: hidden {rel(hid, hid32):.2e}, banks max {max(errs):.2e}")
-    assert rel(hid, hid32) <= 4e-3 and max(errs) <= 3e-3
+    report(f"writer UNet2D full width 96x72: hidden {rel(hid, hid32):.2e}, banks max {max(errs):.2e}")
+    assert rel(hid, hid32) <= 2.5e-3 and max(errs) <= 2e-3
     assert torch.equal(banks[0][0], banks[0][0]) and torch.isfinite(hid).all()
 
 
@@ -211,7 +216,7 @@ def test_pose_guider_and_camera_encoder_golden():
     y = pg(g["x"].cuda().half())
     torch.cuda.synchronize()
     assert y.shape == g["y"].shape
-    assert rel(y, g["y"].cuda()) < 3e-3
+    assert rel(y, g["y"].cuda()) < 1e-3
     g = torch.load(os.path.join(GOLD, "camera_encoder.pt"), weights_only=False)
     o = O.synthetic_init(O.CameraPoseEncoder().eval(), seed=g["seed"])
     cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
@@ -222,7 +227,7 @@ def test_pose_guider_and_camera_encoder_golden():
     y = cam(g["x"].cuda().half())[0]
     torch.cuda.synchronize()
     assert y.shape == g["y"].shape
-    assert rel(y, g["y"].cuda()) < 3e-3
+    assert rel(y, g["y"].cuda()) < 1.5e-3
 
 
 def test_camera_encoder_from_cameras_plucker_on_device():
@@ -257,7 +262,7 @@ def test_camera_encoder_from_cameras_plucker_on_device():
     y_img = cam(gold.transpose(1, 2).contiguous())[0]        # (1, 6, 8, H, W) like scripts/pose2vid.py:285 hands it to the pipeline
     y_cam = cam.forward_cameras(K, c2w, H, W)[0]
     torch.cuda.synchronize()
-    print(f"plucker on device: embedding vs reference golden {e_embed:.2e}; encoder output vs embedding-fed encoder {rel(y_cam, y_img):.2e}")
+    report(f"plucker on device: embedding vs reference golden {e_embed:.2e}; encoder output vs embedding-fed encoder {rel(y_cam, y_img):.2e}")
     assert (un.float() - ref_un.float()).abs().max() <= 2e-3 and e_embed < 3e-4      # fp32 ray arithmetic, differences of one fp16 ulp
     assert y_cam.shape == y_img.shape and rel(y_cam, y_img) < 1e-3
 
@@ -273,7 +278,7 @@ def test_pose_guider_config2_shape_vs_oracle_fp16():
         y = pg(x)
     torch.cuda.synchronize()
     assert y.shape == (1, 320, 4, 96, 72)
-    assert rel(y, ref) < 3e-3
+    assert rel(y, ref) < 1e-3
 
 
 def test_zero_init_modules_are_exact_noops():
