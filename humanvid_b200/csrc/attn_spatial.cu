@@ -443,10 +443,7 @@ attn_kernel8(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 // groups are forced out of phase: a token (two named barriers) lets only one group at a time into its MUFU phase, so one
 // group's max / S / P V latency always hides behind the other group's exponentials, and the K/V tiles are fetched once
 // for 256 queries.  TMEM (512 columns): per group 128 S + 64 P (packed fp16, A operand of the P V MMA) + dv O.
-// warps 0-7 softmax A, 8-15 softmax B (four whole warpgroups), warp 16 TMA, 17 MMA (group A), 18 MMA (group B), 19 idle: the producer
-// warpgroup hands most of its registers to the softmax warpgroups (setmaxnreg: 64 vs 104 per thread), which removes the spills the 96-register
-// budget of a 19-warp CTA forced into the softmax loop (3 % of its executed instructions were LDL / STL)
-constexpr int ATTPP_THREADS = 640;
+constexpr int ATTPP_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax A, warps 10-17 softmax B
 
 template <int D>
 struct PPCfg {
@@ -470,7 +467,7 @@ struct PPCfg {
 // (S_A, P V_A, S_B, P V_B): group B's next S = Q K^T cannot be issued before group A's probabilities arrive, which locks the two groups
 // into the same phase (both in the MUFU phase, then both waiting -- ncu: XU pipe 69 % busy, B waits ~1.7x longer for S than A).
 template <int D, int PE, bool TOKEN, int MW = 1>
-__global__ void __launch_bounds__(ATTPP_THREADS, 1)
+__global__ void __launch_bounds__(ATTPP_THREADS + 32 * (MW - 1), 1)   // 18 (19) warps -> 5 on a scheduler -> 16K / (5 * 32) = 102 -> 96 registers
 attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_kb,
                const __grid_constant__ CUtensorMap map_vbt, const AttnKernelArgs a) {
@@ -521,18 +518,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
   }
-  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // register reallocation (setmaxnreg sits at the top of each role's own branch so that ptxas allocates that region with the new limit):
-  // the CTA owns 640 threads x 96 registers = 61 440; producer warpgroup (warps 16-19) 64 per thread, the 16 softmax warps 104:
-  // 512 * 104 + 128 * 64 = 61 440 exactly (asking for more than the CTA's own pool would spin in setmaxnreg.inc forever)
   // group g: S at +256g (128 columns), P at +256g+128 (64), O at +256g+192 (DV)
 
-  if (warp == 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, 2 * C::kQBytes);
 #pragma unroll
@@ -561,8 +554,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 17 || (MW == 2 && warp == 18)) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  } else if (warp == 1 || warp == 18) {
     {   // all 32 lanes run the issue loop with warp-uniform operands; one elected lane issues (see umma_*_w)
       constexpr uint32_t idesc_pv = umma_idesc_f16(QT, DV);
       constexpr uint32_t idesc_s = umma_idesc_f16(QT, KT);
@@ -593,7 +585,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       tc_fence_after();
       if (MW == 2) {
         // ---- one issuer per group: S(j+1) goes out as soon as the group has read S(j); P V(j) as soon as its P(j) is in TMEM
-        const int g = warp == 17 ? 0 : 1;
+        const int g = warp == 1 ? 0 : 1;
         issue_s(g, 0);
         umma_commit_w(&bar_k_empty[0]);
         for (int j = 0; j < T; ++j) {
@@ -644,19 +636,17 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       }
     }
-  } else if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // idle warp(s) of the producer warpgroup
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ---------------------------------------------------------------- softmax: group g, two threads per query row
-    const int g = warp >> 3;
-    const int w = warp & 7;
+    const int g = (warp - 2) >> 3;
+    const int w = (warp - 2) & 7;
     const int qd = warp & 3;                        // TMEM lane quadrant of this warp
     const int hf = w >> 2;                          // which 64-key half of every tile this thread owns
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * 256, tmem_p = tmem_s + 128, tmem_o = tmem_s + 192;
     const uint32_t my_s = tmem_s + lane_off + hf * 64;
+    float* gmax = smax + g * 512;
     float m_used = -INFINITY;
     const float sc = a.scale_log2;
     // token: barrier 3 = "A may run its MUFU phase", barrier 4 = "B may"; B hands A the first turn
@@ -678,31 +668,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_wait(&bar_s[g], j & 1);
       tc_fence_after();
       tick(0);
-      // pass 1: the row max over all 128 keys of the tile, computed by BOTH threads of the row -- the other half's 64 scores are read from
-      // TMEM for the max only.  (Exchanging two half-row maxima through shared memory cost a 256-thread named barrier per key tile,
-      // ~440 clocks of the ~2600 a tile takes; fmax is exact, so the two threads still agree bit for bit on `grow`.)
+      // pass 1: my half's row max.  The second 32-key chunk stays in registers for pass 2; the first is re-read from
+      // TMEM, the load being issued here so that its latency hides behind the row-max exchange.
       float mx0 = -INFINITY, mx1 = -INFINITY;
       uint32_t raw0[32], raw1[32];
-      {
-        const int kv_other = kv_valid + (2 * hf - 1) * 64;     // valid keys in the other half of the tile
-        tmem_ld32(tmem_s + lane_off + (1 - hf) * 64, raw0);
-        tmem_ld32(tmem_s + lane_off + (1 - hf) * 64 + 32, raw1);
-        tmem_ld_wait();
-        if (64 <= kv_other) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(raw0[i]), __uint_as_float(raw1[i])));
-            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(raw0[i + 1]), __uint_as_float(raw1[i + 1])));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < kv_other) mx0 = fmaxf(mx0, __uint_as_float(raw0[i]));
-            if (32 + i < kv_other) mx1 = fmaxf(mx1, __uint_as_float(raw1[i]));
-          }
-        }
-      }
-      tmem_ld32(my_s, raw0);          // my half: kept in registers for pass 2
+      tmem_ld32(my_s, raw0);
       tmem_ld32(my_s + 32, raw1);
       tmem_ld_wait();
       if (64 <= kv_valid) {
@@ -719,10 +689,20 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       }
       tick(1);
-      const float rowmax = fmaxf(mx0, mx1) * sc;
+      tmem_ld32(my_s, raw0);     // (re-)fetch chunk 0 for pass 2; completes during the exchange below
+      // (measured alternatives, both slower on the same B200: computing the whole row's max in both threads of a row instead of this exchange
+      // + 256-thread barrier costs 64 more TMEM columns and 32 more FMNMX3 per thread-tile: +3 %; re-ordering the warps into four softmax
+      // warpgroups + a producer warpgroup and moving registers to the softmax warps with setmaxnreg (104 / 64) removes the ~50 bytes of
+      // spills of the 96-register build but is another +0.7 %)
+      float* sm = gmax + (j & 1) * 256;
+      sts_f32(sm + hf * 128 + r, fmaxf(mx0, mx1) * sc);
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float rowmax = fmaxf(lds_f32(sm + r), lds_f32(sm + 128 + r));
       const bool grow = rowmax > m_used + kRescaleThreshold;   // identical in both threads of the row
       const float m_new = grow ? rowmax : m_used;
       tick(2);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar_sfree[g]);   // all my reads of S are done: the MMA warp may overwrite it with the next tile's scores
       if (j > 0) {
@@ -826,7 +806,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -851,7 +831,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       const long long nct = static_cast<long long>(grid.x) * grid.y * grid.z;
       if (cudaMalloc(&kd.dbg, nct * 32 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
       cudaMemsetAsync(kd.dbg, 0, nct * 32 * sizeof(long long), stream);
-      attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
+      attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, kd);
       cudaStreamSynchronize(stream);
       long long* hb = static_cast<long long*>(malloc(nct * 32 * sizeof(long long)));
       cudaMemcpy(hb, kd.dbg, nct * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -867,7 +847,7 @@ cudaError_t launch_attn_pp(const CUtensorMap& mq, const CUtensorMap& mk, const C
       cudaFree(kd.dbg);
       return cudaGetLastError();
     }
-    attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS, C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
+    attn_pp_kernel<D, PE, TOKEN, MW><<<grid, ATTPP_THREADS + 32 * (MW - 1), C::kSmemBytes, stream>>>(mq, mk, mvt, mkb, mvbt, ka);
     return cudaGetLastError();
   }
 }
