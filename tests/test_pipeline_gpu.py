@@ -132,3 +132,39 @@ def test_pose2video_pipeline_three_windows_matches_oracle_loop():
     gen = torch.Generator(device=dev).manual_seed(7)
     vid1 = pipe(ref, poses[:24], camera[:, :, :24], W, H, 24, 1, cfg, generator=gen, output_type="tensor").videos
     assert torch.equal(vid, vid1)
+
+
+def test_pose2image_pipeline_call_compatibility():
+    """Pose2ImagePipeline (pipeline_pose2img.py:195-376, BASELINE config 1 plumbing) on the native modules: the reference passes a 4-D
+    camera embedding (b, 6, h, w) and unsqueezes the frame axis itself (:298)."""
+    from humanvid_b200.pipeline import Pose2ImagePipeline
+
+    dev = "cuda"
+    chs, xdim, H, W = (64, 128, 256, 256), 64, 128, 128
+    ora = O.synthetic_init(O.UNet3DConditionModel(block_out_channels=chs, cross_attention_dim=xdim, use_motion_module=False, use_inflated_groupnorm=False).eval(), seed=7)
+    unet = hv.UNet3DConditionModel(block_out_channels=chs, cross_attention_dim=xdim)
+    unet.load_state_dict(ora.state_dict())
+    opg = O.synthetic_init(O.PoseGuider(64, 3, (16, 32, 96, 256)).eval(), seed=11)
+    pg = hv.PoseGuider(64, block_out_channels=(16, 32, 96, 256))
+    pg.load_state_dict(opg.state_dict())
+    ocam = O.synthetic_init(O.CameraPoseEncoder(channels=(64,), heads=8).eval(), seed=13)
+    cam = hv.CameraPoseEncoder(downscale_factor=8, channels=[64], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False, compression_factor=1,
+                               temporal_attention_nhead=8, attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                               temporal_position_encoding_max_len=24)
+    cam.load_state_dict(ocam.state_dict())
+    oref = O.synthetic_init(O.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim).eval(), seed=17)
+    ref_unet = hv.UNet2DConditionModel(block_out_channels=chs, cross_attention_dim=xdim)
+    ref_unet.load_state_dict(oref.state_dict())
+    pipe = Pose2ImagePipeline(vae=StubVAE().half().to(dev), image_encoder=StubCLIP(xdim).half().to(dev), reference_unet=ref_unet, denoising_unet=unet,
+                              pose_guider=pg, camera_pose_encoder=cam, scheduler=hv.DDIMScheduler()).to(dev, torch.float16)
+    g = torch.Generator(device=dev).manual_seed(5)
+    ref = torch.rand(3, H, W, generator=g, device=dev) * 2 - 1
+    pose = torch.rand(1, 3, H, W, generator=g, device=dev)
+    cam4 = torch.randn(1, 6, H, W, generator=g, device=dev).half()
+    gen = torch.Generator(device=dev).manual_seed(1)
+    a = pipe(ref, pose, cam4, W, H, 2, 3.5, generator=gen, output_type="latent", return_dict=False)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    b = pipe(ref, pose, cam4.unsqueeze(2), W, H, 2, 3.5, generator=gen, output_type="latent", return_dict=False)
+    assert a.shape == (1, 4, 1, H // 8, W // 8) and torch.isfinite(a).all() and torch.equal(a, b)
+    img = pipe(ref, pose, cam4, W, H, 1, 3.5, generator=gen, output_type="tensor").images
+    assert img.shape == (1, 3, 1, H, W)
