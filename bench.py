@@ -305,7 +305,8 @@ def time_cond_branches(dev, hbm_gbs, n=5):
     return {"shape": "(1, ., 24, 768, 576)",
             "pose_guider": {"ms": t_pg, "algorithmic_gb": nbytes / 1e9, "gbs": nbytes / 1e6 / t_pg, "frac_of_hbm_peak": nbytes / 1e6 / t_pg / hbm_gbs,
                             "launches": pg.last_launch_count,
-                            "note": "16/32/96-channel activations are padded to 64/64/128 channels for the tcgen05 implicit-GEMM kernel: executed traffic is ~2x the algorithmic bytes"},
+                            "note": "conv_in reads the planar image directly; the 16/32-channel layers run at their true channel counts on the mma.sync small-channel "
+                                    "kernel, the last three (96 -> 96 -> 256 -> 320 at <= 1/4 resolution) on the tcgen05 implicit GEMM"},
             "camera_encoder": {"ms": t_cam, "tflop": 2.18, "tflops": 2.18e3 / t_cam, "launches": cam.last_launch_count},
             "camera_encoder_from_cameras": {"ms": t_rays, "note": "Plucker embedding generated on the device inside the PixelUnshuffle producer (SURVEY 8f-3); "
                                             "the 127 MB (1,6,24,768,576) embedding is never built or copied"}}
@@ -361,7 +362,7 @@ def time_pipeline_clip(dev, unet, steps=25):
     poses = [torch.rand(1, 3, H_, W_, generator=g, device=dev) for _ in range(F_)]
     camera = torch.randn(1, 6, F_, H_, W_, generator=g, device=dev).half()
     out = {}
-    for label, n_steps in (("warmup", 2), ("timed", steps)):
+    for label, n_steps in (("warmup", 2), ("first", steps), ("next", steps)):
         gen = torch.Generator(device=dev).manual_seed(42)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -371,10 +372,11 @@ def time_pipeline_clip(dev, unet, steps=25):
     ok = bool(torch.isfinite(lat).all())
     del pipe, ref_unet, pg, cam
     torch.cuda.empty_cache()
-    return {"steps": steps, "latency_s": out["timed"], "frames_per_s_per_clip": F_ / out["timed"], "denoise_frames_per_s": F_ * steps / out["timed"], "finite": ok,
+    return {"steps": steps, "latency_s": out["next"], "first_clip_latency_s": out["first"], "frames_per_s_per_clip": F_ / out["next"],
+            "denoise_frames_per_s": F_ * steps / out["next"], "finite": ok,
             "what": "humanvid_b200.pipeline.Pose2VideoPipeline.__call__ -> latents: CLIP/VAE stand-ins, native writer UNet2D once, PoseGuider + CameraPoseEncoder once, "
-                    f"{steps} DDIM steps as {steps} replays of one captured CUDA graph (window gather + UNet forward with reference banks + accumulate/CFG/DDIM kernel); "
-                    "wall clock including graph capture"}
+                    f"{steps} DDIM steps as {steps} replays of one captured CUDA graph (window gather + UNet forward with reference banks + accumulate/CFG/DDIM kernel). "
+                    "first_clip_latency_s includes the warm-up step and the graph capture; latency_s is the next clip of the same shape, which reuses the captured step"}
 
 
 def run_native(args, rank, world, local_rank, cfg):
@@ -564,8 +566,10 @@ def run_native(args, rank, world, local_rank, cfg):
 
     frames_total = F if is5 else world * F
     flops_step = cfg["tflop_fwd"] * 1e12 * (len(windows) if is5 else world)
-    skipped_fwd = 2.07 * (H * W) / (96 * 72)   # attn2 to_q / to_out scale with the token count
-    exec_step = flops_step * (1.0 - skipped_fwd / cfg["tflop_fwd"])
+    # executed = what the runtime launched, counted from the unpadded shapes of one profiled forward (rank 0's): the algorithmic count minus attn2's
+    # to_q / to_out over all tokens (one-key cross-attention collapse, -2.07 TF at config 2) and minus 5/9 of the upsampler convs (sub-pixel form)
+    n_fwd_total = (len(windows) if is5 else world)
+    exec_step = executed_fl * n_fwd_total * (2.0 if (is5 and world > 1) else 1.0)   # (a profiled one-half unit is half a window forward)
     value = frames_total / (ms / 1000.0)
     traffic = measured_traffic()
     line = {
@@ -579,8 +583,10 @@ def run_native(args, rank, world, local_rank, cfg):
                    "cond_features": "pose_cond_fea resident (step-invariant; hoisted out of the step as the pipeline's feature cache does)"},
         "tflops_per_step": flops_step / 1e12, "executed_tflops_per_step": exec_step / 1e12,
         "achieved_tflops": exec_step / 1e9 / ms, "frac_of_tensor_roofline_sustained": exec_step / 1e9 / ms / sustained / world,
-        "flops_note": "algorithmic FLOPs per step from SURVEY 8d; `executed` drops attn2's to_q/to_out over all tokens (2.07 TF per forward), which the "
-                      "one-key cross-attention collapse never runs; achieved_tflops and the roofline fraction are on EXECUTED FLOPs",
+        "algorithmic_tflops": flops_step / 1e9 / ms,
+        "flops_note": "tflops_per_step = algorithmic FLOPs of the reference's arithmetic (SURVEY 8d); executed = counted by the runtime from the shapes it launched: "
+                      "no attn2 to_q/to_out over all tokens (one-key cross-attention collapse) and 4/9 of the upsampler-conv multiply-adds (sub-pixel form); "
+                      "achieved_tflops and frac_of_tensor_roofline_sustained are on EXECUTED FLOPs",
         "e2e": {"value": frames_total / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 2),
                 "d2h_bytes_per_step": int(h_out.numel() * 2),
                 "api": ("humanvid_b200.device_loop.DeviceDenoiseLoop step (host latents -> 3 window forwards + glue -> host latents)" if is5 else

@@ -79,6 +79,35 @@ class DeviceDenoiseLoop:
         self._h = None
         self._graph = None
 
+    # ---- reuse for the next clip of the same shape: the captured graph stays valid because every buffer it touches is static ------
+    def signature(self):
+        return (tuple(self.latents.shape), tuple(tuple(w) for w in self.windows), self.cfg_on, self.guidance, tuple(self.scheduler._host_timesteps),
+                self.pred_type, tuple(None if c is None else tuple(c.shape) for c in self.cond), tuple(self.ehs.shape))
+
+    def matches(self, unet, scheduler, latents, windows, encoder_hidden_states, cond_features, guidance_scale, cfg_on) -> bool:
+        return (self._h is not None and unet is self.unet and unet._handle is not None and unet._sync_native().value == self._h.value
+                and self.exchange is None and tuple(latents.shape) == tuple(self.latents.shape)
+                and [list(w) for w in windows] == self.windows and bool(cfg_on) == self.cfg_on and float(guidance_scale) == self.guidance
+                and list(scheduler._host_timesteps) == self.ts.tolist() and tuple(encoder_hidden_states.shape) == tuple(self.ehs.shape)
+                and [None if c is None else tuple(c.shape) for c in cond_features] == [None if c is None else tuple(c.shape) for c in self.cond])
+
+    def reload(self, latents, encoder_hidden_states, cond_features):
+        """New clip, same shapes: copy the inputs into the static buffers the captured step reads, rewind the step counter and hand the
+        (new) reference banks to the handle -- inside the graph the bank pointers are the handle's own buffers, which stay put."""
+        self.latents.copy_(latents.to(torch.float16))
+        self.ehs.copy_(encoder_hidden_states.to(torch.float16))
+        for dst, src in zip(self.cond, cond_features):
+            if dst is not None:
+                dst.copy_(src.to(torch.float16))
+        self.step_index.zero_()
+        self.unet._push_banks(self._h)
+        N.check(N.lib().hv_set_timestep_source(self._h, C.c_void_p(self.ts.data_ptr()), C.c_void_p(self.step_index.data_ptr())), self._h)
+
+    def detach(self):
+        """Between clips: the UNet takes its timestep from the host argument again; buffers and the captured graph are kept."""
+        if self._h is not None and self.unet._handle is not None:
+            N.lib().hv_set_timestep_source(self.unet._handle, None, None)
+
     # ---- one timestep ---------------------------------------------------------------------------------------------
     def _gather(self, w: int, repeat: int) -> torch.Tensor:
         out = torch.empty((repeat * self.Bl, self.Cl, self.Fw, self.H, self.W), device=self.latents.device, dtype=torch.float16)

@@ -122,6 +122,7 @@ class _PipelineBase:
         self.vae_decode_batch = 8
         self.device_step_loop = True     # window gather / accumulate / CFG / DDIM on the device, one CUDA graph per step
         self.use_cuda_graph = True
+        self._cached_loop = None         # the last clip's loop (static buffers + captured graph), reused when the next clip has the same shapes
         self.reference_control_cls = None  # (writer_cls, reader_cls); set by the integrator, see INTEGRATION.md
 
     def to(self, device=None, dtype=None):
@@ -276,12 +277,25 @@ class Pose2VideoPipeline(_PipelineBase):
 
             write_banks()
             conds = [window_features([c]) for c in context_queue]
-            loop = DeviceDenoiseLoop(self.denoising_unet, self.scheduler, latents, context_queue, encoder_hidden_states, conds, guidance_scale, cfg_on,
-                                     **self._loop_kwargs(context_queue, cfg_on))
+            extra = self._loop_kwargs(context_queue, cfg_on)
+            loop = self._cached_loop
+            if loop is not None and not extra and loop.matches(self.denoising_unet, self.scheduler, latents, context_queue, encoder_hidden_states, conds,
+                                                               guidance_scale, cfg_on):
+                # same shapes as the previous clip: the captured step is still valid -- refill its static buffers, no warm-up, no re-capture
+                loop.reload(latents, encoder_hidden_states, conds)
+            else:
+                if loop is not None:
+                    loop.close()
+                loop = DeviceDenoiseLoop(self.denoising_unet, self.scheduler, latents, context_queue, encoder_hidden_states, conds, guidance_scale, cfg_on,
+                                         **extra)
+                self._cached_loop = loop if (self.use_cuda_graph and not extra) else None
             try:
                 latents = loop.run(len(timesteps), use_graph=self.use_cuda_graph).to(latents.dtype).clone()
             finally:
-                loop.close()
+                if self._cached_loop is loop:
+                    loop.detach()
+                else:
+                    loop.close()
             timesteps = []
 
         for i, t in enumerate(timesteps):

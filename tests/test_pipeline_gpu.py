@@ -132,6 +132,21 @@ def test_pose2video_pipeline_three_windows_matches_oracle_loop():
     gen = torch.Generator(device=dev).manual_seed(7)
     vid1 = pipe(ref, poses[:24], camera[:, :, :24], W, H, 24, 1, cfg, generator=gen, output_type="tensor").videos
     assert torch.equal(vid, vid1)
+    # the next clip of the same shape reuses the captured step (static buffers refilled, no warm-up / re-capture) and must give exactly what
+    # a fresh pipeline gives for that clip
+    ref2, poses2, camera2 = ref.flip(-1), poses[::-1], camera.flip(2)
+    gen = torch.Generator(device=dev).manual_seed(9)
+    first = pipe(ref2, poses2, camera2, W, H, Fv, steps, cfg, generator=gen, output_type="latent", return_dict=False)     # (re)captures for 48 frames
+    cached = pipe._cached_loop
+    assert cached is not None and cached._graph is not None
+    gen = torch.Generator(device=dev).manual_seed(11)
+    again = pipe(ref, poses, camera, W, H, Fv, steps, cfg, generator=gen, output_type="latent", return_dict=False)          # reuses it
+    assert pipe._cached_loop is cached
+    fresh = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=ref_unet, denoising_unet=unet, pose_guider=pg, camera_pose_encoder=cam,
+                               scheduler=sched).to(dev, torch.float16)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    expect = fresh(ref, poses, camera, W, H, Fv, steps, cfg, generator=gen, output_type="latent", return_dict=False)
+    assert torch.equal(again, expect) and not torch.equal(again, first)
 
 
 def test_pose2image_pipeline_call_compatibility():
