@@ -95,16 +95,6 @@ __device__ __forceinline__ void store8(__half* dst, const float* v) {
   u.w = pack_h2(v[6], v[7]);
   *reinterpret_cast<uint4*>(dst) = u;
 }
-__device__ __forceinline__ void lds8(const __half* src, float* v) {  // shared memory, 16-byte aligned
-  const uint4 u = *reinterpret_cast<const uint4*>(src);
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __half22float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
 __device__ __forceinline__ void ldsf8(const float* src, float* v) {  // shared memory, 16-byte aligned
   const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
