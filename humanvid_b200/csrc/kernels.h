@@ -9,6 +9,7 @@ cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2,
                              __half* out, int NF, int HW, int groups, float eps, int silu, float* stats, int num_sms,
                              cudaStream_t stream);
 size_t groupnorm_scratch_floats(int C, int NF, int HW, int groups, int num_sms);
+int groupnorm_num_launches(int C, int NF, int HW, int num_sms);
 cudaError_t launch_layernorm(const __half* x, const __half* gamma, const __half* beta, __half* out, long long rows, int C, float eps,
                              const __half* pre_add, long long rows_per_group, __half* x_out, const __half* pe, int hw, int F,
                              cudaStream_t stream);

@@ -555,7 +555,7 @@ struct hv_model {
     Tens out = alloc_act(x.NF, x.H, x.W, x.C + C2);
     float* stats = static_cast<float*>(ar.alloc(sizeof(float) * groupnorm_scratch_floats(x.C + C2, x.NF, x.H * x.W, cfg.norm_groups, sms)));
     if (ar.dry) return out;
-    launches += 2;
+    launches += groupnorm_num_launches(x.C + C2, x.NF, x.H * x.W, sms);
     Timed tm(this, CAT_NORM, 0, "groupnorm", x.rows(), x.C + C2, 0);
     ck(launch_groupnorm(x.p, x.C, x2 ? x2->p : nullptr, C2, n.g, n.b, out.p, x.NF, x.H * x.W, cfg.norm_groups, n.eps, silu ? 1 : 0, stats, sms, st),
        "groupnorm");

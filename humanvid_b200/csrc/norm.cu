@@ -108,6 +108,33 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
   const int n = blockIdx.y;
   const int rl = threadIdx.x / vecs, v = threadIdx.x % vecs, rpi = blockDim.x / vecs;
   const int c0 = v * 8;
+  // {mean, rstd} of this frame's groups: four lanes per group add the per-slab partial sums (each lane its slabs in order, then a fixed
+  // two-step tree -> deterministic), full warps only so that the shuffles are well defined whatever the block size
+  extern __shared__ float2 sstat[];   // [groups]
+  {
+    const int full = (blockDim.x >> 5) << 5;
+    if (static_cast<int>(threadIdx.x) < full) {
+      for (int g0 = 0; g0 < groups; g0 += full / 4) {
+        const int g = g0 + static_cast<int>(threadIdx.x) / 4, l = threadIdx.x & 3;
+        float ss = 0.f, qq = 0.f;
+        if (g < groups)
+          for (int sl = l; sl < slabs; sl += 4) {
+            const float2 pp = __ldg(reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * slabs + sl) * groups + g) * 2));
+            ss += pp.x;
+            qq += pp.y;
+          }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+        if (g < groups && l == 0) {
+          const float mean = ss * inv_cnt;
+          sstat[g] = make_float2(mean, rsqrtf(fmaxf(qq * inv_cnt - mean * mean, 0.f) + eps));
+        }
+      }
+    }
+    __syncthreads();
+  }
   float sc[8], sh[8];
   {
     float gm[8], bt[8];
@@ -115,16 +142,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, const __h
     unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c0)), bt);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      // finalize folded in: add this (frame, group)'s per-slab partial sums in slab order (fixed order -> deterministic) -> mean, rstd
-      const int g = (c0 + 2 * k) / cpg;
-      float ss = 0.f, qq = 0.f;
-      for (int sl = 0; sl < slabs; ++sl) {
-        const float2 pp = __ldg(reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * slabs + sl) * groups + g) * 2));
-        ss += pp.x;
-        qq += pp.y;
-      }
-      const float mean = ss * inv_cnt;
-      const float2 st = make_float2(mean, rsqrtf(fmaxf(qq * inv_cnt - mean * mean, 0.f) + eps));
+      const float2 st = sstat[(c0 + 2 * k) / cpg];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         sc[2 * k + j] = st.y * gm[2 * k + j];
@@ -247,9 +265,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 }  // namespace
 
 // scratch floats needed by launch_groupnorm: final {mean, rstd} + per-slab partials
+// The split of a frame's rows into slabs (= the order its statistics are summed in) depends on HW only, never on the number of frames in
+// the batch: a forward of one CFG half (a unit of the multi-GPU split) is then bitwise equal to that half of a CFG batch.
+// (Measured and rejected: normalising ~56 MB chunks of frames at a time so that the apply pass re-reads from L2 what the statistics pass
+// just pulled in -- the smaller launches lose far more bandwidth than the L2 hits return: 135 us -> 250 us at level 0.)
 static void gn_plan(int C, int NF, int HW, int num_sms, int* threads, int* slabs, int* rows_per_block) {
-  // The split of a frame's rows into slabs (= the order its statistics are summed in) depends on HW only, never on the number of
-  // frames in the batch: a forward of one CFG half (a unit of the multi-GPU split) is then bitwise equal to that half of a CFG batch.
   (void)NF;
   (void)num_sms;
   const int vecs = C / 8;
@@ -269,6 +289,8 @@ size_t groupnorm_scratch_floats(int C, int NF, int HW, int groups, int num_sms) 
   return static_cast<size_t>(2) * NF * groups * (1 + sl);
 }
 
+int groupnorm_num_launches(int, int, int, int) { return 2; }
+
 cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2, const __half* gamma, const __half* beta,
                              __half* out, int NF, int HW, int groups, float eps, int silu, float* stats, int num_sms,
                              cudaStream_t stream) {
@@ -278,12 +300,12 @@ cudaError_t launch_groupnorm(const __half* x1, int C1, const __half* x2, int C2,
   if (vecs > 1024) return cudaErrorInvalidValue;
   int threads, slabs, rows_per_block;
   gn_plan(C, NF, HW, num_sms, &threads, &slabs, &rows_per_block);
-  if (threads < groups) return cudaErrorInvalidValue;
+  if (threads < groups || threads < 32) return cudaErrorInvalidValue;
   float* partial = stats + static_cast<size_t>(2) * NF * groups;
   gn_stats_kernel<<<dim3(slabs, NF), threads, threads * 8 * sizeof(float), stream>>>(x1, C1, x2, C2, HW, groups, rows_per_block, partial);
   // (the {mean, rstd} finalize is folded into the apply kernel: one launch less per GroupNorm, 83 per forward)
-  gn_apply_kernel<<<dim3(slabs, NF), threads, 0, stream>>>(x1, C1, x2, C2, gamma, beta, out, HW, groups, rows_per_block, silu, partial, slabs,
-                                                           1.f / (static_cast<float>(HW) * (C / groups)), eps);
+  gn_apply_kernel<<<dim3(slabs, NF), threads, groups * sizeof(float2), stream>>>(x1, C1, x2, C2, gamma, beta, out, HW, groups, rows_per_block, silu, partial,
+                                                                                 slabs, 1.f / (static_cast<float>(HW) * (C / groups)), eps);
   return cudaGetLastError();
 }
 
