@@ -316,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         __syncwarp();
       }
       const bool ts = MT == 1 && e.tma_io != 0;
-      int ts_col0 = 0, ts_row0 = 0;
+      int ts_col0 = 0, ts_row0 = 0, ts_batch = 0;
       uint8_t* io = io_base + (warp - 2) * C::kIoPerWarp;
       if (ts) {
         // ---- 128-row linear tiles: this warp's 32 x SL slice goes through its shared-memory box; the residual slice is
@@ -326,6 +326,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         const bool has_res = e.residual != nullptr && !e.geglu;
         ts_row0 = tc.m0 + q * 32;
         ts_col0 = e.geglu ? n_blk * (BLOCK_N / 2) + cs * (BLOCK_N / 8) : n_blk * BLOCK_N + cs * SL;
+        if (p.b_batch) {                                 // batched B (V^T): column inside the batch item's segment + the item (3-D output map)
+          ts_col0 = (n_blk % n_per_batch) * BLOCK_N + cs * SL;
+          ts_batch = n_blk / n_per_batch;
+        }
         if (lane == 0) {
           tma_store_wait_read();                         // the previous tile's store has drained the box
           if (has_res) {
@@ -592,7 +596,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       if (lane == 0) {
         mbar_arrive(&bar_tempty[acc]);
         if (ts) {
-          tma_store_2d(&map_out, io, ts_col0, ts_row0);
+          if (p.b_batch) tma_store_3d(&map_out, io, ts_col0, ts_row0, ts_batch);
+          else tma_store_2d(&map_out, io, ts_col0, ts_row0);
           tma_store_commit();
         }
       }
@@ -714,7 +719,7 @@ cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   if (p.cluster && !(m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && gemm_wants_cluster(p.M, p.N, block_n, m_sub, false)))
     return cudaErrorInvalidValue;   // the caller built 64-row A boxes for a launch that cannot use them
   GemmEpilogue e = e_in;
-  e.tma_io = (io_out != nullptr && m_sub == 1 && p.a_mode == A_LINEAR && !p.b_batch && (e.residual == nullptr || e.geglu || io_res != nullptr)) ? 1 : 0;
+  e.tma_io = (io_out != nullptr && m_sub == 1 && p.a_mode == A_LINEAR && (e.residual == nullptr || e.geglu || io_res != nullptr)) ? 1 : 0;
   const CUtensorMap& mo = e.tma_io ? *io_out : a0;
   const CUtensorMap& mr = (e.tma_io && io_res) ? *io_res : mo;
   const int tile_m = BLOCK_M * m_sub;

@@ -49,6 +49,14 @@ bool make_map_2d_box(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return encode(m, ptr, 2, dims, strides, box);
 }
 
+bool make_map_3d_io(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int64_t batch, int64_t row_stride, int64_t batch_stride, int box_rows,
+                    int box_cols) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return encode(m, ptr, 3, dims, strides, box, swz);
+}
 bool make_map_2d_io(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};

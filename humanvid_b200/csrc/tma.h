@@ -28,6 +28,10 @@ bool make_map_3d(CUtensorMap* m, const void* ptr, int64_t batch, int64_t rows, i
 // Epilogue I/O box of the GEMM (TMA store of the output tile / TMA load of the residual tile): fp16 [rows][ld] with `cols`
 // valid columns, box = box_rows x box_cols, shared-memory rows of box_cols * 2 bytes (128 -> 128B swizzle, 64 -> 64B swizzle,
 // anything else unswizzled).  Out-of-range rows / columns are clipped on store and read as zero on load.
+// The same for the batched-B GEMM (V^T producer): out[row][b * batch_stride + col], col < cols: 3-D map (cols, rows, batch), box
+// (box_cols, box_rows, 1).  Columns beyond `cols` are clipped per batch item, so a frame's ragged last tile never spills into the next frame.
+bool make_map_3d_io(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int64_t batch, int64_t row_stride, int64_t batch_stride, int box_rows,
+                    int box_cols);
 bool make_map_2d_io(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
 // Token matrix [frames][pixels][ld] (cols valid) viewed along the frame axis: 3-D map (cols, pixels, frames), unswizzled box
