@@ -379,6 +379,43 @@ def time_pipeline_clip(dev, unet, steps=25):
                     "first_clip_latency_s includes the warm-up step and the graph capture; latency_s is the next clip of the same shape, which reuses the captured step"}
 
 
+def gemm_classes(trace_path, tensor_peak, hbm_peak):
+    """Splits the launches of the dominant kernel family (gemm_kernel: linears, 1x1 / 3x3 / sub-pixel convs, V^T) by what bounds them.  A launch whose
+    arithmetic intensity (FLOPs / compulsory HBM bytes: A read once, output written once, residual read once, fp16) is below 1.5x the machine
+    balance (peak TF/s / peak TB/s) is HBM-bound and is scored in GB/s against the measured copy bandwidth; the rest are scored in TF/s against the
+    sustained tensor peak."""
+    import csv
+
+    balance = tensor_peak * 1e12 / (hbm_peak * 1e9)
+    cls = {"tensor_bound": [0.0, 0.0, 0.0, 0], "hbm_bound": [0.0, 0.0, 0.0, 0]}   # ms, flops, bytes, launches
+    try:
+        rows = list(csv.DictReader(open(trace_path)))
+    except Exception:
+        return None
+    for r in rows:
+        lb = r["label"]
+        if int(r["cat"]) not in (0, 1) or not lb:
+            continue
+        M, Nn, K, ms = float(r["M"]), float(r["N"]), float(r["K"]), float(r["ms"])
+        if lb == "gemm_vt":            # out[M rows][N tokens] = W[M][K] . X[N][K]^T
+            fl, by = 2 * M * Nn * K, 2 * (Nn * K + M * Nn)
+        elif lb.startswith("conv3") or lb.startswith("upconv") or lb.startswith("smallconv") or lb == "pg_conv_in":
+            taps = 4 if lb.startswith("upconv") else 9
+            cin = K / taps
+            rows_in = M / 4 if lb.startswith("upconv") else (M * 4 if lb.endswith("_s2") else M)
+            fl, by = 2 * M * Nn * K, 2 * (rows_in * cin + M * Nn * (2 if lb.endswith("_res") else 1))
+        else:
+            n_out = Nn / 2 if lb == "gemm_geglu" else Nn
+            fl, by = 2 * M * Nn * K, 2 * (M * K + M * n_out * (2 if lb == "gemm_res" else 1))
+        c = cls["hbm_bound" if fl / by < 1.5 * balance else "tensor_bound"]
+        c[0] += ms; c[1] += fl; c[2] += by; c[3] += 1
+    t, h = cls["tensor_bound"], cls["hbm_bound"]
+    return {"machine_balance_flop_per_byte": balance,
+            "tensor_bound": {"launches": t[3], "ms": t[0], "tflops": t[1] / 1e9 / t[0] if t[0] else None, "frac_of_tensor_peak": t[1] / 1e9 / t[0] / tensor_peak if t[0] else None},
+            "hbm_bound": {"launches": h[3], "ms": h[0], "gbs": h[2] / 1e6 / h[0] if h[0] else None, "frac_of_hbm_peak": h[2] / 1e6 / h[0] / hbm_peak if h[0] else None,
+                          "tflops": h[1] / 1e9 / h[0] if h[0] else None}}
+
+
 def run_native(args, rank, world, local_rank, cfg):
     import ctypes as C
 
@@ -539,9 +576,10 @@ def run_native(args, rank, world, local_rank, cfg):
         unet(x1, 500, ehs, pose_cond_fea=poses[0], return_dict=False)
     cat_ms, cat_fl, cat_n = (C.c_double * 6)(), (C.c_double * 6)(), (C.c_int64 * 6)()
     N.check(lib.hv_get_profile(unet._handle, cat_ms, cat_fl, cat_n, 6), unet._handle)
-    if os.environ.get("HV_TRACE"):
-        lib.hv_dump_profile(unet._handle, os.environ["HV_TRACE"].encode())
+    trace_path = os.environ.get("HV_TRACE") or os.path.join("/tmp", f"hv_trace_{os.getpid()}.csv")
+    lib.hv_dump_profile(unet._handle, trace_path.encode())
     lib.hv_set_profiling(unet._handle, 0)
+    classes = gemm_classes(trace_path, *peaks()[:1], peaks()[2])
     names = ["tcgen05_gemm_linear", "tcgen05_implicit_gemm_conv3x3", "tcgen05_spatial_attention", "temporal_attention", "norms", "small_linear"]
     prof = {names[i]: {"ms": round(cat_ms[i], 3), "tflop": round(cat_fl[i] / 1e12, 3), "launches": int(cat_n[i]),
                        "tflops": round(cat_fl[i] / 1e9 / cat_ms[i], 1) if cat_ms[i] > 0 else None} for i in range(6)}
@@ -596,7 +634,7 @@ def run_native(args, rank, world, local_rank, cfg):
                      "unit": "TFLOP/s", "frac": achieved / sustained, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src_pk})",
                      "launches_per_forward": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_tflop_per_forward": gemm_fl / 1e12,
                      "traffic": (traffic or {}).get("gemm_kernel_avg_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                     "executed_tflop_per_forward_all_kernels": executed_fl / 1e12},
+                     "executed_tflop_per_forward_all_kernels": executed_fl / 1e12, "by_bound": classes},
         "op_profile": prof,
         "clocks": clocks,
     }
