@@ -63,7 +63,8 @@ class DeviceDenoiseLoop:
         self.ehs = encoder_hidden_states.to(torch.float16).contiguous()
         self.cond = [None if c is None else c.to(torch.float16).contiguous() for c in cond_features]
         self.coef = scheduler.coef_table().to(dev).contiguous()                      # [steps][4] fp32
-        self.ts = torch.tensor(scheduler._host_timesteps, dtype=torch.int64, device=dev)
+        self._ts_host = [int(t) for t in scheduler._host_timesteps]
+        self.ts = torch.tensor(self._ts_host, dtype=torch.int64, device=dev)
         self.step_index = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pred_type = {"v_prediction": 0, "epsilon": 1}[scheduler.config.prediction_type]
         self.exchange, self.my_units, self.all_units = exchange, my_units, all_units
@@ -88,7 +89,7 @@ class DeviceDenoiseLoop:
         return (self._h is not None and unet is self.unet and unet._handle is not None and unet._sync_native().value == self._h.value
                 and self.exchange is None and tuple(latents.shape) == tuple(self.latents.shape)
                 and [list(w) for w in windows] == self.windows and bool(cfg_on) == self.cfg_on and float(guidance_scale) == self.guidance
-                and list(scheduler._host_timesteps) == self.ts.tolist() and tuple(encoder_hidden_states.shape) == tuple(self.ehs.shape)
+                and [int(t) for t in scheduler._host_timesteps] == self._ts_host and tuple(encoder_hidden_states.shape) == tuple(self.ehs.shape)
                 and [None if c is None else tuple(c.shape) for c in cond_features] == [None if c is None else tuple(c.shape) for c in self.cond])
 
     def reload(self, latents, encoder_hidden_states, cond_features):

@@ -21,6 +21,7 @@ import ctypes as C
 import json
 import math
 import os
+import warnings
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import List, Optional, Sequence, Tuple, Union
@@ -466,6 +467,15 @@ class UNet3DConditionModel(_NativeNet):
         self._bank_fp, self._bank_refs = fp, tensors
         N.check(lib.hv_clear_ref_banks(h), h)
         if not any_bank:
+            # A reader control is registered (ours, or the reference's: its register_reference_hooks leaves an instance-level `forward` on every
+            # block, mutual_self_attention.py:302-330) but no bank has been written: the reference would then attend over the clip's own tokens
+            # only, and so does this forward -- legal, but almost always a missing `reader.update(writer)`.  Say so once.
+            hooked = getattr(self, "_reader_registered", False) or any("forward" in b.__dict__ for b in blocks)
+            if hooked and not getattr(self, "_warned_no_bank", False):
+                self._warned_no_bank = True
+                warnings.warn("humanvid_b200.UNet3DConditionModel: a ReferenceAttentionControl reader is registered but every reference bank is "
+                              "empty; this forward runs without reference attention (call reader.update(writer) after the writer forward)",
+                              RuntimeWarning, stacklevel=3)
             return
         st = N.stream()
         for i, b in enumerate(blocks):
@@ -922,6 +932,7 @@ class ReferenceAttentionControl:
             if not isinstance(unet, UNet3DConditionModel):
                 raise TypeError("mode='read' needs a humanvid_b200.UNet3DConditionModel")
             unet._ref_cfg = bool(do_classifier_free_guidance)
+            unet._reader_registered = True
             for m in unet.reader_blocks():
                 m.bank = []
         else:

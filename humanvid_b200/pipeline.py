@@ -8,7 +8,9 @@ UNet stay whatever PyTorch modules the caller passes (the reference's own); the 
 
 Differences from the reference that do not change results: pose / camera features are computed once per context window
 and reused across timesteps when ``cache_condition_features=True`` (the reference recomputes the step-invariant
-features every step, :526-537); the reference's stray ``print`` calls are dropped.
+features every step, :526-537); the reference's stray ``print`` calls are dropped.  One deliberate deviation: the reference's
+window-batching loop reuses the name ``i`` (:511-517), so its ``callback`` receives ``num_context_batches - 1`` instead of the step index;
+here ``callback(i, t, latents)`` gets the true step index.  A callback (or eta != 0, or unequal windows) selects the host loop below.
 """
 from __future__ import annotations
 

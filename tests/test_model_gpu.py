@@ -298,3 +298,16 @@ def test_too_many_frames_is_an_error(narrow):
     x, ehs, pose = unet_inputs(2, 33, 16, 16, 64, 64)
     with pytest.raises(RuntimeError, match="max_len"):
         nat(x, 10, ehs, pose_cond_fea=pose)
+
+
+def test_registered_reader_with_empty_banks_warns_once():
+    # a reader control without a written bank must not be silent
+    _, nat = make_unet((64, 128, 256, 256), 64, seed=5)
+    hv.ReferenceAttentionControl(nat, mode="read", do_classifier_free_guidance=True, fusion_blocks="full")
+    x, ehs, pose = unet_inputs(2, 4, 16, 16, 64, 64)
+    with pytest.warns(RuntimeWarning, match="reference bank is empty"):
+        nat(x, 10, ehs, pose_cond_fea=pose)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        nat(x, 11, ehs, pose_cond_fea=pose)   # once per model
