@@ -1,8 +1,11 @@
 """ncu metrics pass (dram bytes + duration per launch) of one bench step -> profiles/r02_dram_traffic.{json,txt}.
 
-    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --launch-skip 1700 --launch-count 1700 \
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'hv::' \
         --csv --log-file gpurun_out/dram.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager --no-extras
-    python scripts/summarize_dram.py gpurun_out/dram.csv profiles/r02_dram_traffic
+    python scripts/summarize_dram.py gpurun_out/dram.csv profiles/r02_dram_traffic [launch_list.csv]
+
+Every launch of the library in that process is captured; the summary covers the LAST complete UNet forward (from the last
+`timestep_embedding` launch to the end).  With a third argument the per-launch list of that forward is written too.
 """
 import collections
 import csv
@@ -19,7 +22,7 @@ def family(name):
     return re.sub(r"<.*", "", name.split("(")[0]).strip()[-40:]
 
 
-def main(src, dst):
+def main(src, dst, listing=None):
     rows = []
     with open(src, newline="") as f:
         lines = [l for l in f if not l.startswith("==")]
@@ -41,6 +44,19 @@ def main(src, dst):
         if "duration" in m:
             v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1)   # -> ms
         per[lid][m] = v
+    ids = sorted(per, key=int)
+    starts = [i for i in ids if "timestep_embedding" in names[i]]
+    if starts:                                    # the last complete forward
+        ids = [i for i in ids if int(i) >= int(starts[-1])]
+    per = {i: per[i] for i in ids}
+    if listing:
+        with open(listing, "w") as f:
+            f.write("# one UNet forward of `bench.py --steps 1` (config 2): ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                    "--clock-control none (cold-cache serialised replays)\nid,kernel,time_us,dram_read_MB,dram_write_MB\n")
+            for n, i in enumerate(ids):
+                m = per[i]
+                f.write(f"{n},{re.sub(r'^.*hv::', '', names[i].split('(')[0])[:60]},{m.get('gpu__time_duration.sum', 0) * 1e3:.2f},"
+                        f"{m.get('dram__bytes_read.sum', 0) / 1e6:.1f},{m.get('dram__bytes_write.sum', 0) / 1e6:.1f}\n")
     fam = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for lid, m in per.items():
         f = fam[family(names[lid])]
@@ -66,4 +82,4 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])
