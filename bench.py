@@ -379,41 +379,47 @@ def time_pipeline_clip(dev, unet, steps=25):
                     "first_clip_latency_s includes the warm-up step and the graph capture; latency_s is the next clip of the same shape, which reuses the captured step"}
 
 
+HBM_WRITE_GBS = 3924.0   # write-only ceiling of this pool's B200 (profiles/r02_hbm_ceilings.txt, scripts/write_bw.py); reads: MEASURED_PEAKS hbm_gbs
+
+
 def gemm_classes(trace_path, tensor_peak, hbm_peak):
-    """Splits the launches of the dominant kernel family (gemm_kernel: linears, 1x1 / 3x3 / sub-pixel convs, V^T) by what bounds them.  A launch whose
-    arithmetic intensity (FLOPs / compulsory HBM bytes: A read once, output written once, residual read once, fp16) is below 1.5x the machine
-    balance (peak TF/s / peak TB/s) is HBM-bound and is scored in GB/s against the measured copy bandwidth; the rest are scored in TF/s against the
-    sustained tensor peak."""
+    """Scores every launch of the dominant kernel family (gemm_kernel: linears, 1x1 / 3x3 / sub-pixel convs, V^T) against ITS OWN roofline:
+    t_tensor = FLOPs / sustained tensor peak, t_hbm = compulsory reads / read bandwidth + compulsory writes / write-only bandwidth (fp16; A read
+    once, residual read once, output written once; weights stay in L2).  The larger of the two is the launch's bound; launches are grouped by which
+    one it is.  `frac_of_shape_roofline` = sum of the bounds / sum of the measured times over all launches."""
     import csv
 
-    balance = tensor_peak * 1e12 / (hbm_peak * 1e9)
-    cls = {"tensor_bound": [0.0, 0.0, 0.0, 0], "hbm_bound": [0.0, 0.0, 0.0, 0]}   # ms, flops, bytes, launches
     try:
         rows = list(csv.DictReader(open(trace_path)))
     except Exception:
         return None
+    cls = {"tensor_bound": [0, 0.0, 0.0, 0.0, 0.0], "hbm_bound": [0, 0.0, 0.0, 0.0, 0.0]}   # launches, ms, bound ms, flops, bytes
     for r in rows:
         lb = r["label"]
         if int(r["cat"]) not in (0, 1) or not lb:
             continue
         M, Nn, K, ms = float(r["M"]), float(r["N"]), float(r["K"]), float(r["ms"])
+        fl = 2 * M * Nn * K
         if lb == "gemm_vt":            # out[M rows][N tokens] = W[M][K] . X[N][K]^T
-            fl, by = 2 * M * Nn * K, 2 * (Nn * K + M * Nn)
-        elif lb.startswith("conv3") or lb.startswith("upconv") or lb.startswith("smallconv") or lb == "pg_conv_in":
+            rd, wr = 2 * Nn * K, 2 * M * Nn
+        elif lb.startswith("conv3") or lb.startswith("upconv"):
             taps = 4 if lb.startswith("upconv") else 9
-            cin = K / taps
             rows_in = M / 4 if lb.startswith("upconv") else (M * 4 if lb.endswith("_s2") else M)
-            fl, by = 2 * M * Nn * K, 2 * (rows_in * cin + M * Nn * (2 if lb.endswith("_res") else 1))
+            rd, wr = 2 * (rows_in * K / taps + (M * Nn if lb.endswith("_res") else 0)), 2 * M * Nn
         else:
             n_out = Nn / 2 if lb == "gemm_geglu" else Nn
-            fl, by = 2 * M * Nn * K, 2 * (M * K + M * n_out * (2 if lb == "gemm_res" else 1))
-        c = cls["hbm_bound" if fl / by < 1.5 * balance else "tensor_bound"]
-        c[0] += ms; c[1] += fl; c[2] += by; c[3] += 1
+            rd, wr = 2 * (M * K + (M * n_out if lb == "gemm_res" else 0)), 2 * M * n_out
+        t_tensor = fl / (tensor_peak * 1e9)                       # ms
+        t_hbm = rd / (hbm_peak * 1e6) + wr / (HBM_WRITE_GBS * 1e6)
+        c = cls["hbm_bound" if t_hbm > t_tensor else "tensor_bound"]
+        c[0] += 1; c[1] += ms; c[2] += max(t_tensor, t_hbm); c[3] += fl; c[4] += rd + wr
     t, h = cls["tensor_bound"], cls["hbm_bound"]
-    return {"machine_balance_flop_per_byte": balance,
-            "tensor_bound": {"launches": t[3], "ms": t[0], "tflops": t[1] / 1e9 / t[0] if t[0] else None, "frac_of_tensor_peak": t[1] / 1e9 / t[0] / tensor_peak if t[0] else None},
-            "hbm_bound": {"launches": h[3], "ms": h[0], "gbs": h[2] / 1e6 / h[0] if h[0] else None, "frac_of_hbm_peak": h[2] / 1e6 / h[0] / hbm_peak if h[0] else None,
-                          "tflops": h[1] / 1e9 / h[0] if h[0] else None}}
+    tot_ms, tot_bound = t[1] + h[1], t[2] + h[2]
+    return {"hbm_read_gbs": hbm_peak, "hbm_write_gbs": HBM_WRITE_GBS, "hbm_write_source": "profiles/r02_hbm_ceilings.txt (scripts/write_bw.py, measured on this pool)",
+            "frac_of_shape_roofline": tot_bound / tot_ms if tot_ms else None,
+            "tensor_bound": {"launches": t[0], "ms": t[1], "bound_ms": t[2], "tflops": t[3] / 1e9 / t[1] if t[1] else None, "frac": t[2] / t[1] if t[1] else None},
+            "hbm_bound": {"launches": h[0], "ms": h[1], "bound_ms": h[2], "gbs": h[4] / 1e6 / h[1] if h[1] else None, "tflops": h[3] / 1e9 / h[1] if h[1] else None,
+                          "frac": h[2] / h[1] if h[1] else None}}
 
 
 def run_native(args, rank, world, local_rank, cfg):
