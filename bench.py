@@ -193,6 +193,8 @@ def workload_name(cfg, world):
         return (f"config5: 1 clip x 48 frames 576x1024 (latent 72x128), 3 context windows of 24 frames per timestep (context.py), CFG batch 2{banks}, "
                 f"random-init UNet3D 1.31B params" + (f"; the 6 (window x CFG-half) units split over {world} GPUs" if world > 1 else ""))
     per = "1 clip/GPU" if world > 1 else "1 clip"
+    if cfg.get("single_clip"):
+        per = f"ONE clip, its 2 CFG halves split over {world} GPUs (ranks beyond 2 idle),"
     return f"{cfg['name']}: {per} x 24 frames 768x576 (latent 96x72), CFG batch 2, random-init UNet3D 1.31B params{banks}"
 
 
@@ -441,7 +443,8 @@ def run_native(args, rank, world, local_rank, cfg):
 
         dist.init_process_group("nccl", device_id=dev)
 
-    is5 = cfg["name"] == "config5"
+    # one clip over all ranks (strong scaling): config 5 always; configs 2 / 3 with --single-clip (1 window x 2 CFG halves = the 2-GPU CFG split)
+    is5 = cfg["name"] == "config5" or (args.single_clip and world > 1)
     F, Fw, H, W = cfg["frames"], cfg["fw"], cfg["h"], cfg["w"]
     unet = build_native(dev)
     # config 5 is ONE clip (same data on every rank); configs 2-4 are one clip per rank (seed 42 + rank)
@@ -515,12 +518,14 @@ def run_native(args, rank, world, local_rank, cfg):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for _ in range(args.steps):
-                if is5:   # one GPU doing all units would be the config-5 N = 1 run; here: this rank's share only
-                    break
-                out = step()
+                if is5:   # one clip: the step's window forwards at the full CFG batch on this GPU alone (the N = 1 run minus its ~0.1 ms of glue)
+                    for wi in range(len(windows)):
+                        unet(sample, 500, ehs, pose_cond_fea=poses[wi], return_dict=False)
+                else:
+                    out = step()
             s1.record()
             torch.cuda.synchronize()
-            solo_ms = None if is5 else s0.elapsed_time(s1) / args.steps
+            solo_ms = s0.elapsed_time(s1) / args.steps
         barrier()
 
     # ---- kernel-only: inputs resident, K steps bracketed by barrier + synchronize, device-timed
@@ -633,7 +638,7 @@ def run_native(args, rank, world, local_rank, cfg):
                       "achieved_tflops and frac_of_tensor_roofline_sustained are on EXECUTED FLOPs",
         "e2e": {"value": frames_total / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 2),
                 "d2h_bytes_per_step": int(h_out.numel() * 2),
-                "api": ("humanvid_b200.device_loop.DeviceDenoiseLoop step (host latents -> 3 window forwards + glue -> host latents)" if is5 else
+                "api": (f"humanvid_b200.device_loop.DeviceDenoiseLoop step (host latents -> {len(windows)} window forward(s) + glue -> host latents)" if is5 else
                         "humanvid_b200.UNet3DConditionModel.forward (host latents -> host prediction)")},
         "gpu_launches": int(launches_step) * args.steps,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<128|160|256> (tcgen05 GEMM + implicit-GEMM conv3x3)", "achieved": achieved, "peak": sustained,
@@ -645,7 +650,11 @@ def run_native(args, rank, world, local_rank, cfg):
         "clocks": clocks,
     }
     line.update(extras)
-    if solo_ms is not None:
+    if solo_ms is not None and is5:
+        line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s", "speedup_vs_solo": solo_ms / ms,
+                              "efficiency_vs_solo": solo_ms / ms / world, "ideal_speedup": min(world, len(windows) * 2),
+                              "what": "the same clip's step (all window forwards at the full CFG batch) on rank 0 alone, the other GPUs idle, in this run"}
+    elif solo_ms is not None:
         line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s",
                               "efficiency_vs_solo": value / (world * F / (solo_ms / 1000.0)),
                               "what": "the same per-GPU workload (one config-3 clip) timed on rank 0 with the other GPUs idle, in this run: the N = 1 reference of THIS "
@@ -668,6 +677,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--single-clip", action="store_true",
+                    help="with --gpus N > 1 and --config 2|3: ONE clip over the ranks ((window x CFG-half) unit split, SURVEY 8f-4) instead of one clip per rank")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5], help="BASELINE config; default 2 on one GPU, 4 (= N x config 3) on N > 1")
     ap.add_argument("--banks", type=int, default=0, help="legacy: 1 = config 3")
@@ -683,11 +694,13 @@ def main():
     c = args.config or (3 if args.banks else (4 if n > 1 else 2))
     if c == 4 and n == 1:
         c = 3
-    if c in (2, 3) and n > 1:
+    if c in (2, 3) and n > 1 and not args.single_clip:
         c = 4 if c == 3 else 2   # N > 1 with --config 2 keeps banks off (the round-1 scaling workload)
     cfg = dict(CONFIGS[c])
-    if c == 2 and n > 1:
+    if c == 2 and n > 1 and not args.single_clip:
         cfg["name"] = "config2 per GPU"
+    if args.single_clip and n > 1 and c in (2, 3):
+        cfg["single_clip"] = True
     if args.impl == "reference":
         run_reference(args, rank, cfg)
         return
