@@ -86,7 +86,7 @@ def test_unit_split_matches_single_process(tmp_path):
         preds = {(w, h): _fake_unet(lat, windows[w], h, t) for w in range(len(windows)) for h in (0, 1)}
         lat = _glue_reference(lat, preds, windows, 3.5, [float(c) for c in coefs[step]])
     assert torch.equal(r[0]["lat"], lat) and torch.equal(r[1]["lat"], lat)          # replicated and identical to one process
-    assert r[0]["mine"] == [(0, 0), (1, 0), (2, 0)] and r[1]["mine"] == [(0, 1), (1, 1), (2, 1)]
+    assert r[0]["mine"] == [(0, 1), (2, 0), (2, 1)] and r[1]["mine"] == [(0, 0), (1, 0), (1, 1)]   # cost-balanced, not round-robin
     for k in range(world):
         assert torch.equal(r[0]["clips"][k], lat[0, :, :3] * (k + 1))
         assert torch.equal(r[1]["clips"], r[0]["clips"])
@@ -95,8 +95,14 @@ def test_unit_split_matches_single_process(tmp_path):
 def test_assignment_and_inverse_map():
     units = unit_list(3, True)
     assert [len(a) for a in assign_units(units, 8)] == [1, 1, 1, 1, 1, 1, 0, 0]
-    assert [len(a) for a in assign_units(units, 4)] == [2, 2, 1, 1]
-    assert sorted(u for a in assign_units(units, 4) for u in a) == sorted(units)
+    for world in (1, 2, 3, 4, 6, 8):                          # a partition of the units, balanced by cost (conditional units are heavier)
+        asg = assign_units(units, world)
+        assert sorted(u for a in asg for u in a) == sorted(units)
+        conds = [sum(1 for u in a if u[1] == 1) for a in asg]
+        assert max(conds) - min(c for c, a in zip(conds, asg) if a or world <= 6) <= 1 or world > 6
+        assert max(len(a) for a in asg) == -(-len(units) // world)
+    assert [len(a) for a in assign_units(units, 4)] == [2, 1, 1, 2]
+    assert [sum(u[1] for u in a) for a in assign_units(units, 2)] == [2, 1]   # never all three conditional units on one rank
     ex = UnitExchange(units, world=1, rank=0)                 # degenerate world: no collective, same mapping
     got = ex([torch.full((2, 2), float(i)) for i in range(6)])
     assert all(float(got[u][0, 0]) == i for i, u in enumerate(units))
