@@ -40,6 +40,12 @@ def uniform(step: int = 0, num_steps: Optional[int] = None, num_frames: int = 0,
             yield [e % num_frames for e in range(j, j + context_size * context_step, context_step)]
 
 
+def get_total_steps(scheduler, timesteps, num_steps: Optional[int] = None, num_frames: int = 0, context_size: Optional[int] = None,
+                    context_stride: int = 3, context_overlap: int = 4, closed_loop: bool = True) -> int:
+    """context.py:50-76: number of UNet calls of a whole loop (note: like the reference, `closed_loop` is accepted and not forwarded)."""
+    return sum(len(list(scheduler(i, num_steps, num_frames, context_size, context_stride, context_overlap))) for i in range(len(timesteps)))
+
+
 # ---- latent interpolation (src/pipelines/utils.py) -----------------------------------------------------------------
 tensor_interpolation = None
 
