@@ -1,6 +1,9 @@
 """Isolated timing of hv_op_gemm at the L0 linear shapes, with epilogue pieces switched off one by one."""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import humanvid_b200._native as _N
+if os.environ.get("HV_LIB"):   # A/B against another build of the library (e.g. the tuning build)
+    _N.LIB_PATH = os.environ["HV_LIB"]
 from humanvid_b200._native import Epilogue, check, i64, lib, ptr, stream
 
 def bench(M, N, K, bias=True, res=True, n_valid=0, iters=20, geglu=False):
