@@ -3,7 +3,7 @@
 // channels to the 64-channel k-block of the tcgen05 implicit-GEMM kernel moved 2-4x the necessary bytes (round 1: PoseGuider ran at
 // 4.6 % of HBM speed on its algorithmic bytes).  Here they run at their true channel counts:
 //
-//   pg_conv_in_kernel            Cin = 3, read straight from the (B, 3, F, H, W) pose image (no layout pass), one thread per pixel
+//   pg_conv_in_kernel            Cin = 3, read straight from the (B, 3, F, H, W) pose image (no layout pass), mma.sync with K = 27 -> 32
 //   smallconv_mma_kernel<CIN, COUT, STRIDE>
 //                                channels-last fp16, implicit GEMM on mma.sync.m16n8k16 (the problems are far below a tcgen05 tile):
 //                                a CTA stages the (8 x 32 output) tile's input halo in shared memory with cp.async (zero fill = padding),
@@ -142,64 +142,107 @@ smallconv_mma_kernel(const __half* __restrict__ x, const __half* __restrict__ wp
   }
 }
 
-// conv_in of the PoseGuider: (B, 3, F, H, W) fp16 planes -> channels-last (B*F, H, W, 16), 3x3, padding 1, + bias, SiLU.
-// One thread = two horizontally adjacent pixels x 16 channels: every weight fetched from shared memory (a broadcast LDS) feeds two FMAs
-// -- with one pixel per thread the kernel was bound by the 432 LDS per pixel, not by its 432 FMAs or its 64 + 340 MB of traffic.
+// conv_in of the PoseGuider: (B, 3, F, H, W) fp16 planes -> channels-last (B*F, H, W, 16), 3x3, padding 1, + bias, SiLU -- as an implicit
+// GEMM on mma.sync.m16n8k16: M = pixels, N = 16, K = (ci, ky, kx) = 27 padded to 32 (the weight tensor (16, 3, 3, 3) IS the [n][k] operand).
+// A block stages the 3 x (8 + 2) x (64 + 2) input halo of an 8 x 64 output tile in shared memory (zero fill = padding); a warp owns one
+// output row = four m16 tiles; a lane builds its A fragment from 16 two-byte shared loads at compile-time-constant tap offsets (no im2col
+// buffer), the 8 B-fragment registers are loaded once per thread.  Rows leave through shared memory as 16-byte coalesced stores.
+// (The SIMT version before this one -- one thread = two pixels x 16 channels, 432 FMAs and 216 broadcast LDS per pixel -- ran at 0.65 ms
+// for 64 + 340 MB at (1,3,24,768,576): 6.5 % of HBM speed, bound by instruction issue; profiles/r02_ncu_cond_branches.txt.)
+constexpr int PG_TH = 8, PG_TW = 64, PG_ROWS = PG_TH + 2, PG_COLS = PG_TW + 2, PG_RS = PG_TW + 4, PG_OP = 24;   // PG_OP: halves per staged output pixel (16 + 8 pad: conflict-free)
+
 __global__ void __launch_bounds__(256) pg_conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
-                                                         __half* __restrict__ out, int B, int F, int H, int W, int act) {
-  __shared__ float ws[16 * 27 + 16];
-  for (int i = threadIdx.x; i < 16 * 27; i += blockDim.x) ws[i] = __half2float(w[i]);   // (16, 3, 3, 3) as is: [co][ci][ky][kx]
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) ws[16 * 27 + i] = bias ? __half2float(bias[i]) : 0.f;
-  __syncthreads();
-  const int W2 = (W + 1) / 2;
-  const long long HW = static_cast<long long>(H) * W, total = static_cast<long long>(B) * F * H * W2;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xx = static_cast<int>(i % W2) * 2;
-    long long t = i / W2;
-    const int yy = static_cast<int>(t % H);
-    const long long nf = t / H;
-    const int b = static_cast<int>(nf / F), f = static_cast<int>(nf % F);
-    float in[3][3][4];   // [ci][ky][columns xx-1 .. xx+2]
+                                                         __half* __restrict__ out, int B, int F, int H, int W, int act, int tiles_x, int tiles_y) {
+  __shared__ __align__(16) __half tile[3 * PG_ROWS * PG_RS];
+  __shared__ __align__(16) __half ostage[8][PG_TW * PG_OP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long HW = static_cast<long long>(H) * W;
+
+  // ---- per-thread constants: B fragments (weights as [n][k], k >= 27 is zero) and the shared-memory offsets of this lane's 8 k indices
+  uint32_t bf[2][2][2];   // [k16 step][n8 tile][k half]
+  int koff[2][2][2];      // [k16 step][k half][element]
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-      const __half* plane = x + ((static_cast<long long>(b) * 3 + ci) * F + f) * HW;
+  for (int s = 0; s < 2; ++s)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int gy = yy + ky - 1;
+    for (int h = 0; h < 2; ++h) {
+      const int k0 = s * 16 + h * 8 + 2 * t;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int gx = xx + c - 1;
-          in[ci][ky][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __half2float(__ldg(plane + static_cast<long long>(gy) * W + gx)) : 0.f;
-        }
+      for (int e = 0; e < 2; ++e) {
+        const int k = k0 + e;
+        koff[s][h][e] = k < 27 ? ((k / 9) * PG_ROWS + (k % 9) / 3) * PG_RS + (k % 3) : 0;   // k >= 27: any finite value, its weight is zero
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __half lo = k0 < 27 ? w[(j * 8 + g) * 27 + k0] : __float2half(0.f);
+        const __half hi = k0 + 1 < 27 ? w[(j * 8 + g) * 27 + k0 + 1] : __float2half(0.f);
+        bf[s][j][h] = static_cast<uint32_t>(__half_as_ushort(lo)) | (static_cast<uint32_t>(__half_as_ushort(hi)) << 16);
       }
     }
-    uint32_t o0[8], o1[8];
+  float bia[2][2];
 #pragma unroll
-    for (int cp = 0; cp < 8; ++cp) {
-      float a0 = ws[16 * 27 + 2 * cp], a1 = ws[16 * 27 + 2 * cp + 1], b0 = a0, b1 = a1;   // pixel xx: a*, pixel xx + 1: b*
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float w0 = ws[(2 * cp) * 27 + ci * 9 + ky * 3 + kx], w1 = ws[(2 * cp + 1) * 27 + ci * 9 + ky * 3 + kx];
-            a0 = fmaf(in[ci][ky][kx], w0, a0);
-            a1 = fmaf(in[ci][ky][kx], w1, a1);
-            b0 = fmaf(in[ci][ky][kx + 1], w0, b0);
-            b1 = fmaf(in[ci][ky][kx + 1], w1, b1);
-          }
-      if (act == 2) { a0 = silu_f(a0); a1 = silu_f(a1); b0 = silu_f(b0); b1 = silu_f(b1); }
-      o0[cp] = pack_h2(a0, a1);
-      o1[cp] = pack_h2(b0, b1);
+  for (int j = 0; j < 2; ++j) {
+    bia[j][0] = bias ? __half2float(bias[j * 8 + 2 * t]) : 0.f;
+    bia[j][1] = bias ? __half2float(bias[j * 8 + 2 * t + 1]) : 0.f;
+  }
+
+  const long long ntiles = static_cast<long long>(B) * F * tiles_y * tiles_x;
+  for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int tx = static_cast<int>(tl % tiles_x);
+    long long r = tl / tiles_x;
+    const int ty = static_cast<int>(r % tiles_y);
+    const long long nf = r / tiles_y;
+    const int b = static_cast<int>(nf / F), f = static_cast<int>(nf % F);
+    const int y0 = ty * PG_TH, x0 = tx * PG_TW;
+
+    // ---- stage the halo of the three input planes; outside the image = the conv's zero padding
+    for (int i = tid; i < 3 * PG_ROWS * PG_COLS; i += 256) {
+      const int c = i % PG_COLS;
+      const int rr = (i / PG_COLS) % PG_ROWS;
+      const int ci = i / (PG_COLS * PG_ROWS);
+      const int gy = y0 - 1 + rr, gx = x0 - 1 + c;
+      __half v = __float2half(0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(x + ((static_cast<long long>(b) * 3 + ci) * F + f) * HW + static_cast<long long>(gy) * W + gx);
+      tile[(ci * PG_ROWS + rr) * PG_RS + c] = v;
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((nf * H + yy) * W + xx) * 16);
-    dst[0] = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-    dst[1] = make_uint4(o0[4], o0[5], o0[6], o0[7]);
-    if (xx + 1 < W) {
-      dst[2] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-      dst[3] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+    __syncthreads();
+
+    // ---- this warp: output row y0 + warp, 64 pixels = four m16 tiles
+    const unsigned short* tl16 = reinterpret_cast<const unsigned short*>(tile);
+    __half* orow = ostage[warp];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int pa = warp * PG_RS + mt * 16 + g, pb = pa + 8;
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        uint32_t a[4];
+        a[0] = static_cast<uint32_t>(tl16[koff[s][0][0] + pa]) | (static_cast<uint32_t>(tl16[koff[s][0][1] + pa]) << 16);   // row g,     k = 2t, 2t+1
+        a[1] = static_cast<uint32_t>(tl16[koff[s][0][0] + pb]) | (static_cast<uint32_t>(tl16[koff[s][0][1] + pb]) << 16);   // row g + 8
+        a[2] = static_cast<uint32_t>(tl16[koff[s][1][0] + pa]) | (static_cast<uint32_t>(tl16[koff[s][1][1] + pa]) << 16);   // row g,     k = 2t+8, 2t+9
+        a[3] = static_cast<uint32_t>(tl16[koff[s][1][0] + pb]) | (static_cast<uint32_t>(tl16[koff[s][1][1] + pb]) << 16);   // row g + 8
+        mma_16816(acc[0], a, bf[s][0][0], bf[s][0][1]);
+        mma_16816(acc[1], a, bf[s][1][0], bf[s][1][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v0 = acc[j][2 * h] + bia[j][0], v1 = acc[j][2 * h + 1] + bia[j][1];
+          if (act == 2) { v0 = silu_f(v0); v1 = silu_f(v1); } else if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          *reinterpret_cast<uint32_t*>(orow + (mt * 16 + g + 8 * h) * PG_OP + j * 8 + 2 * t) = pack_h2(v0, v1);
+        }
     }
+    __syncwarp();
+    const int y = y0 + warp;
+    if (y < H) {
+      __half* dst = out + ((static_cast<size_t>(nf) * H + y) * W + x0) * 16;
+      for (int i = lane; i < PG_TW * 2; i += 32) {
+        const int p = i >> 1, c = i & 1;
+        if (x0 + p < W) *reinterpret_cast<uint4*>(dst + p * 16 + c * 8) = *reinterpret_cast<const uint4*>(orow + p * PG_OP + c * 8);
+      }
+    }
+    __syncthreads();   // every warp is done with the halo (and its staging row) before the next tile overwrites them
   }
 }
 
@@ -239,10 +282,11 @@ cudaError_t launch_smallconv(const __half* x, const __half* wp, const __half* bi
 
 cudaError_t launch_pg_conv_in(const __half* x, const __half* w, const __half* bias, __half* out, int B, int F, int H, int W, int act, int num_sms,
                               cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * F * H * ((W + 1) / 2);
-  long long blocks = (total + 255) / 256;
-  if (blocks > static_cast<long long>(num_sms) * 32) blocks = static_cast<long long>(num_sms) * 32;
-  pg_conv_in_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, out, B, F, H, W, act);
+  const int tiles_x = (W + PG_TW - 1) / PG_TW, tiles_y = (H + PG_TH - 1) / PG_TH;
+  long long blocks = static_cast<long long>(B) * F * tiles_y * tiles_x;
+  if (blocks > static_cast<long long>(num_sms) * 7) blocks = static_cast<long long>(num_sms) * 7;   // 7 x 28.6 KB of static shared memory per SM
+  if (blocks < 1) return cudaErrorInvalidValue;
+  pg_conv_in_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, out, B, F, H, W, act, tiles_x, tiles_y);
   return cudaGetLastError();
 }
 

@@ -166,15 +166,19 @@ class _PipelineBase:
         enc_dtype = next(self.image_encoder.parameters()).dtype if hasattr(self.image_encoder, "parameters") else torch.float16
         return self.image_encoder(pix.to(device, dtype=enc_dtype)).image_embeds
 
-    def _device_loop_ok(self, eta, callback, context_batch_size, context_queue, latents) -> bool:
+    def _device_loop_ok(self, eta, callback, context_batch_size, context_queue, latents, cfg_on=True) -> bool:
         """The on-device loop covers what scripts/pose2vid.py uses: native denoising UNet, this package's DDIM scheduler with
-        eta = 0, no per-step host callback, one window per UNet call, equally long windows."""
+        eta = 0, no per-step host callback, one window per UNet call, equally long windows, and CFG on whenever windows overlap.
+        (Without CFG the reference never divides the accumulated prediction by ``counter`` -- the division sits inside the CFG branch,
+        pipeline_pose2vid_long.py:551-555 -- so overlapping windows are SUMMED; the glue kernel always averages, so that corner is
+        left to the host loop below, which restates the reference line by line.)"""
         from .modules import UNet3DConditionModel
         from .scheduler import DDIMScheduler
 
         return (self.device_step_loop and isinstance(self.denoising_unet, UNet3DConditionModel) and isinstance(self.scheduler, DDIMScheduler)
                 and eta == 0.0 and callback is None and context_batch_size == 1 and latents.is_cuda
-                and len({len(c) for c in context_queue}) == 1 and len(context_queue) <= 32)
+                and len({len(c) for c in context_queue}) == 1 and len(context_queue) <= 32
+                and (cfg_on or len(context_queue) == 1))
 
     def _loop_kwargs(self, context_queue, cfg_on):
         """Extra DeviceDenoiseLoop arguments; humanvid_b200.distributed overrides this to split (window x CFG-half) units over ranks."""
@@ -279,7 +283,7 @@ class Pose2VideoPipeline(_PipelineBase):
 
         # the scheduler is always asked with step = 0 (:495-502): the windows are the same at every timestep
         context_queue = list(context_scheduler(0, num_inference_steps, latents.shape[2], context_frames, context_stride, context_overlap))
-        if self._device_loop_ok(eta, callback, context_batch_size, context_queue, latents):
+        if self._device_loop_ok(eta, callback, context_batch_size, context_queue, latents, cfg_on):
             # ---- every per-timestep operation on the device, one CUDA graph per step -------------------------
             from .device_loop import DeviceDenoiseLoop
 

@@ -152,15 +152,23 @@ def test_conv3x3_small_channels_mma(NF, H, W, Cin, Cout, stride):
     assert bool((out[..., Cout:] == 7.0).all())     # pad columns untouched
 
 
-def test_pose_conv_in_from_planar_image():
-    B, Fr, H, W = 1, 3, 40, 56
+@pytest.mark.parametrize("B,Fr,H,W", [(1, 3, 40, 56), (2, 2, 19, 130), (1, 1, 8, 64), (1, 4, 128, 1152), (1, 1, 5, 7)])
+def test_pose_conv_in_from_planar_image(B, Fr, H, W):
+    """pose_guider.py:25 conv_in (3 -> 16) + SiLU straight from the planar image: tiles of 8 x 64 outputs, ragged edges, several batch items,
+    more tiles than resident blocks."""
     img = torch.rand(B, 3, Fr, H, W, device="cuda").half()
     w, b = dev(16, 3, 3, 3, scale=0.2, seed=36), dev(16, seed=37)
-    out = torch.zeros(B * Fr, H, W, 16, device="cuda", dtype=torch.half)
+    out = torch.full((B * Fr, H, W, 16), 9.0, device="cuda", dtype=torch.half)
     check(lib().hv_op_pose_conv_in(ptr(img), ptr(w), ptr(b), ptr(out), i64(B), i64(Fr), i64(H), i64(W), i32(2), stream()))
-    ref = F.silu(F.conv2d(img[0].permute(1, 0, 2, 3).float(), w.float(), b.float(), padding=1)).permute(0, 2, 3, 1)
+    ref = torch.cat([F.silu(F.conv2d(img[i].permute(1, 0, 2, 3).float(), w.float(), b.float(), padding=1)).permute(0, 2, 3, 1) for i in range(B)])
     torch.cuda.synchronize()
     assert rel(out, ref) < 1e-3
+    assert float((out.float() - ref).abs().max()) < 4e-3      # every pixel, edges included (fp16 half-ulp of |y| <= 4 is 1e-3)
+    out2 = torch.empty_like(out)
+    check(lib().hv_op_pose_conv_in(ptr(img), ptr(w), ptr(None), ptr(out2), i64(B), i64(Fr), i64(H), i64(W), i32(0), stream()))   # no bias, no activation
+    ref2 = torch.cat([F.conv2d(img[i].permute(1, 0, 2, 3).float(), w.float(), None, padding=1).permute(0, 2, 3, 1) for i in range(B)])
+    torch.cuda.synchronize()
+    assert rel(out2, ref2) < 1e-3
 
 
 def test_conv3x3_direct_small_channels():
