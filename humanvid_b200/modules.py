@@ -612,7 +612,7 @@ class UNet3DConditionModel(_NativeNet):
                 raise RuntimeError(f"unknown file format for motion module weights: {suffix}")
             if mm_zero_proj_out:
                 mm_state = {k: v for k, v in mm_state.items() if "proj_out" not in k}
-            state.update({k: v for k, v in mm_state.items() if "motion_modules" in k})
+            state.update(mm_state)   # every key, like the reference (unet_3d.py:657-658); load_state_dict(strict=False) drops what the model lacks
         model.load_state_dict(state, strict=False)
         return model
 

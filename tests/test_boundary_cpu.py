@@ -139,3 +139,69 @@ def test_pipeline_windows_match_oracle():
 
     for nf in (24, 48, 87):
         assert [list(w) for w in uniform(0, 25, nf, 24, 1, 4)] == O.uniform_windows(0, nf, 24, 1, 4)
+
+
+def test_from_pretrained_2d_loading_flow(tmp_path):
+    """unet_3d.py:579-670: config.json -> model, 2-D weights (.safetensors preferred, else .bin), motion-module file merged on top (every key,
+    `proj_out` keys dropped under mm_zero_proj_out), strict=False; same exceptions for a missing config / weights file / unknown suffix."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from humanvid_b200 import UNet3DConditionModel
+
+    mmk = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+               temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+    extra = dict(use_motion_module=True, use_inflated_groupnorm=True, motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True,
+                 motion_module_type="Vanilla", motion_module_kwargs=mmk, unet_use_cross_frame_attention=False, unet_use_temporal_attention=False)
+    src = O.synthetic_init(O.UNet3DConditionModel(block_out_channels=(32, 64, 128, 128), cross_attention_dim=64), seed=3)
+    full = {k: v.clone() for k, v in src.state_dict().items()}
+    sd2d = {k: v.contiguous() for k, v in full.items() if "motion_modules" not in k}
+    mm = {k: v.contiguous() for k, v in full.items() if "motion_modules" in k}
+    root = tmp_path / "sd15"
+    (root / "unet").mkdir(parents=True)
+    cfg = {"_class_name": "UNet2DConditionModel", "_diffusers_version": "0.6.0", "in_channels": 4, "out_channels": 4, "block_out_channels": [32, 64, 128, 128],
+           "cross_attention_dim": 64, "attention_head_dim": 8, "layers_per_block": 2, "norm_num_groups": 32, "act_fn": "silu",
+           "down_block_types": ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], "up_block_types": ["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3,
+           "sample_size": 64, "some_future_key": 1}
+    json.dump(cfg, open(root / "unet" / "config.json", "w"))
+    mm_file = tmp_path / "mm.ckpt"
+    torch.save(mm, mm_file)
+
+    with pytest.raises(FileNotFoundError):
+        UNet3DConditionModel.from_pretrained_2d(root, mm_file, subfolder="unet", unet_additional_kwargs=extra)
+    torch.save(sd2d, root / "unet" / "diffusion_pytorch_model.bin")
+    m = UNet3DConditionModel.from_pretrained_2d(root, mm_file, subfolder="unet", unet_additional_kwargs=extra)
+    got = m.state_dict()
+    assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in full)
+    assert m.config.sample_size == 64 and m.config.block_out_channels == [32, 64, 128, 128]
+
+    # .safetensors wins over .bin when both exist
+    marked = {k: (v + 1.0 if k == "conv_in.bias" else v) for k, v in sd2d.items()}
+    save_file(marked, str(root / "unet" / "diffusion_pytorch_model.safetensors"))
+    m2 = UNet3DConditionModel.from_pretrained_2d(root, mm_file, subfolder="unet", unet_additional_kwargs=extra)
+    assert torch.equal(m2.state_dict()["conv_in.bias"], full["conv_in.bias"] + 1.0)
+
+    # mm_zero_proj_out: the motion modules' proj_out stay at their zero init (identity modules), everything else is loaded
+    m3 = UNet3DConditionModel.from_pretrained_2d(root, mm_file, subfolder="unet", unet_additional_kwargs=extra, mm_zero_proj_out=True)
+    for k, v in m3.state_dict().items():
+        if "motion_modules" in k and "proj_out" in k:
+            assert float(v.abs().sum()) == 0.0, k
+        elif "motion_modules" in k:
+            assert torch.equal(v, full[k]), k
+
+    # a missing motion-module file is not an error (the reference only checks exists() and is_file()): motion modules keep their init
+    m4 = UNet3DConditionModel.from_pretrained_2d(root, tmp_path / "absent.ckpt", subfolder="unet", unet_additional_kwargs=extra)
+    assert float(m4.state_dict()["mid_block.motion_modules.0.temporal_transformer.proj_out.weight"].abs().sum()) == 0.0
+
+    # a key of the motion-module file that the 2-D file also has overrides it (state_dict.update of every key)
+    torch.save({**mm, "conv_in.bias": full["conv_in.bias"] + 2.0}, tmp_path / "mm_plus.ckpt")
+    m5 = UNet3DConditionModel.from_pretrained_2d(root, tmp_path / "mm_plus.ckpt", subfolder="unet", unet_additional_kwargs=extra)
+    assert torch.equal(m5.state_dict()["conv_in.bias"], full["conv_in.bias"] + 2.0)
+
+    bad = tmp_path / "mm.weights"
+    bad.write_bytes(b"x")
+    with pytest.raises(RuntimeError):
+        UNet3DConditionModel.from_pretrained_2d(root, bad, subfolder="unet", unet_additional_kwargs=extra)
+    with pytest.raises(RuntimeError):
+        UNet3DConditionModel.from_pretrained_2d(tmp_path / "nowhere", mm_file, unet_additional_kwargs=extra)
