@@ -63,7 +63,8 @@ class DDIMScheduler:
     def scale_model_input(self, sample, timestep=None):
         return sample
 
-    def step(self, model_output, timestep, sample, eta=0.0, generator=None, **_):
+    def step(self, model_output, timestep, sample, eta=0.0, use_clipped_model_output=False, generator=None, variance_noise=None, return_dict=True):
+        """diffusers' ``DDIMScheduler.step`` signature; ``return_dict=False`` returns ``(prev_sample,)`` (pipeline_pose2img.py:351-353 indexes it)."""
         if eta != 0.0:
             raise NotImplementedError("eta != 0")
         t = int(timestep)
@@ -80,4 +81,6 @@ class DDIMScheduler:
         else:
             raise NotImplementedError(pt)
         prev_sample = (a_p**0.5) * x0 + ((1 - a_p) ** 0.5) * eps
+        if not return_dict:
+            return (prev_sample.to(sample.dtype),)
         return SimpleNamespace(prev_sample=prev_sample.to(sample.dtype), pred_original_sample=x0)
