@@ -307,8 +307,8 @@ def time_cond_branches(dev, hbm_gbs, n=5):
     return {"shape": "(1, ., 24, 768, 576)",
             "pose_guider": {"ms": t_pg, "algorithmic_gb": nbytes / 1e9, "gbs": nbytes / 1e6 / t_pg, "frac_of_hbm_peak": nbytes / 1e6 / t_pg / hbm_gbs,
                             "launches": pg.last_launch_count,
-                            "note": "conv_in reads the planar image directly; the 16/32-channel layers run at their true channel counts on the mma.sync small-channel "
-                                    "kernel, the last three (96 -> 96 -> 256 -> 320 at <= 1/4 resolution) on the tcgen05 implicit GEMM"},
+                            "note": "conv_in reads the planar image directly (mma.sync implicit GEMM, K = 27 -> 32); the 16/32-channel layers run at their true channel counts on "
+                                    "the mma.sync small-channel kernel, the last three (96 -> 96 -> 256 -> 320 at <= 1/4 resolution) on the tcgen05 implicit GEMM"},
             "camera_encoder": {"ms": t_cam, "tflop": 2.18, "tflops": 2.18e3 / t_cam, "launches": cam.last_launch_count},
             "camera_encoder_from_cameras": {"ms": t_rays, "note": "Plucker embedding generated on the device inside the PixelUnshuffle producer (SURVEY 8f-3); "
                                             "the 127 MB (1,6,24,768,576) embedding is never built or copied"}}
