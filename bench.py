@@ -508,7 +508,7 @@ def run_native(args, rank, world, local_rank, cfg):
     n_fwd = (len(loop.my_units) if (is5 and world > 1) else len(windows)) if is5 else 1
     launches_step = launches_fwd * n_fwd + ((n_fwd + 2) if is5 else 0)
 
-    # ---- (N > 1) the same per-GPU workload on rank 0 ALONE, the other GPUs idle: the reference point for scaling efficiency on THIS workload
+    # ---- (N > 1) the same per-GPU workload on rank 0 ALONE, the other GPUs idle: the single-GPU reference point of THIS workload (no ratio is reported: the driver computes scaling itself)
     # (the default N = 1 run is config 2, the N > 1 runs are config 4 = N x config 3, which has 10 % more work per GPU)
     solo_ms = None
     if world > 1:
@@ -651,12 +651,10 @@ def run_native(args, rank, world, local_rank, cfg):
     }
     line.update(extras)
     if solo_ms is not None and is5:
-        line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s", "speedup_vs_solo": solo_ms / ms,
-                              "efficiency_vs_solo": solo_ms / ms / world, "ideal_speedup": min(world, len(windows) * 2),
+        line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s", "independent_units": len(windows) * 2,
                               "what": "the same clip's step (all window forwards at the full CFG batch) on rank 0 alone, the other GPUs idle, in this run"}
     elif solo_ms is not None:
         line["solo_rank0"] = {"ms_per_step": solo_ms, "value": F / (solo_ms / 1000.0), "unit": "frames/s",
-                              "efficiency_vs_solo": value / (world * F / (solo_ms / 1000.0)),
                               "what": "the same per-GPU workload (one config-3 clip) timed on rank 0 with the other GPUs idle, in this run: the N = 1 reference of THIS "
                                       "workload (the default N = 1 bench line is config 2, 10 % less work per GPU)"}
     if eager is not None:
