@@ -235,12 +235,18 @@ class _NativeNet(nn.Module):
 
     def _versions(self):
         # fingerprint checked on every forward: in-place edits of ANY parameter / buffer (sum of their version counters), a
-        # re-allocation or dtype change of the first one, and load_state_dict()/.to()/.half() (the epoch) all force a re-push
-        p = next(self.parameters())
+        # re-allocation or dtype change of the first one, and load_state_dict()/.to()/.half() (the epoch) all force a re-push.
+        # The flat tensor list is cached per epoch: walking the module tree (~600 modules, 1270 tensors) cost 3 ms of host time per
+        # forward, which the end-to-end step (copy in -> forward -> copy out, nothing to hide behind) paid in full.  A Parameter OBJECT
+        # replaced by attribute assignment is not seen by the cache: call refresh_native() after such surgery (in-place edits are seen).
+        cache = self.__dict__.get("_ver_cache")
+        if cache is None or cache[0] != self._epoch:
+            cache = (self._epoch, list(self.parameters()) + list(self.buffers()))
+            self.__dict__["_ver_cache"] = cache
+        tensors = cache[1]
+        p = tensors[0]
         ver = 0
-        for t in self.parameters():
-            ver += t._version
-        for t in self.buffers():
+        for t in tensors:
             ver += t._version
         return (p.data_ptr(), ver, p.dtype, self._epoch)
 
@@ -451,8 +457,12 @@ class UNet3DConditionModel(_NativeNet):
                 out += dfs(c)
             return out
 
-        mods = [m for m in dfs(self) if isinstance(m, TemporalBasicTransformerBlock)]
-        return sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
+        cached = self.__dict__.get("_reader_blocks_cache")
+        if cached is None:      # the module tree is fixed after __init__: walk it once (1 ms per forward otherwise)
+            mods = [m for m in dfs(self) if isinstance(m, TemporalBasicTransformerBlock)]
+            cached = sorted(mods, key=lambda m: -m.norm1.normalized_shape[0])
+            self.__dict__["_reader_blocks_cache"] = cached
+        return list(cached)
 
     def _push_banks(self, h):
         lib = N.lib()

@@ -205,3 +205,49 @@ def test_from_pretrained_2d_loading_flow(tmp_path):
         UNet3DConditionModel.from_pretrained_2d(root, bad, subfolder="unet", unet_additional_kwargs=extra)
     with pytest.raises(RuntimeError):
         UNet3DConditionModel.from_pretrained_2d(tmp_path / "nowhere", mm_file, unet_additional_kwargs=extra)
+
+
+def test_native_fingerprint_tracks_parameter_edits():
+    """_NativeNet._versions() decides on every forward whether the packed device weights are stale.  Its tensor list is cached per epoch
+    (3 ms of module-tree walking per forward otherwise); the fingerprint must still move on an in-place edit of ANY parameter or buffer, on
+    load_state_dict(), on .to() / .half(), on refresh_native() -- and must not move otherwise."""
+    from humanvid_b200 import PoseGuider, UNet3DConditionModel
+
+    mmk = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+               temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1)
+    m = UNet3DConditionModel(block_out_channels=(32, 64, 64, 64), cross_attention_dim=32, use_motion_module=True, use_inflated_groupnorm=True,
+                             motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=True, motion_module_type="Vanilla", motion_module_kwargs=mmk)
+    v0 = m._versions()
+    assert m._versions() == v0 and m._versions() == v0                               # stable
+    n_tensors = len(list(m.parameters())) + len(list(m.buffers()))
+    assert len(m.__dict__["_ver_cache"][1]) == n_tensors
+    with torch.no_grad():
+        m.up_blocks[3].attentions[2].transformer_blocks[0].ff.net[2].bias.add_(1.0)   # a deep parameter, edited in place
+    v1 = m._versions()
+    assert v1 != v0
+    with torch.no_grad():
+        m.mid_block.motion_modules[0].temporal_transformer.transformer_blocks[0].attention_blocks[1].pos_encoder.pe.mul_(0.5)   # a buffer
+    v2 = m._versions()
+    assert v2 != v1
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    v3 = m._versions()
+    assert v3 != v2 and v3[3] == v2[3] + 1
+    m.half()
+    v4 = m._versions()
+    assert v4 != v3 and v4[2] == torch.float16
+    assert all(t.dtype == torch.float16 for t in m.__dict__["_ver_cache"][1] if t.is_floating_point())   # the cache was rebuilt on the new tensors
+    m.refresh_native()
+    assert m._versions() != v4
+    # reader blocks: cached walk == the reference's order (DFS down, up, mid; stable sort by descending width), a fresh list every call
+    a, b = m.reader_blocks(), m.reader_blocks()
+    assert a == b and a is not b and len(a) == 16
+    assert [x.norm1.normalized_shape[0] for x in a] == [64] * 11 + [32] * 5
+    names = {id(mod): n for n, mod in m.named_modules()}
+    assert [names[id(x)] for x in a][:3] == ["down_blocks.1.attentions.0.transformer_blocks.0", "down_blocks.1.attentions.1.transformer_blocks.0",
+                                             "down_blocks.2.attentions.0.transformer_blocks.0"]
+    pg = PoseGuider(320, block_out_channels=(16, 32, 96, 256))
+    p0 = pg._versions()
+    with torch.no_grad():
+        pg.blocks[3].weight.zero_()
+    assert pg._versions() != p0
